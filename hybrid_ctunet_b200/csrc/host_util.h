@@ -1,0 +1,18 @@
+// Host-side helpers shared by the launchers: driver entry point for TMA descriptor encoding, launch counter.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <atomic>
+#include <stdint.h>
+
+namespace ctu {
+
+typedef CUresult (*tma_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled, looked up through the runtime so the library does not link against libcuda.
+tma_encode_fn tma_encoder();
+void count_launch(int n = 1);
+
+}  // namespace ctu

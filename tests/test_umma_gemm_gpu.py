@@ -1,0 +1,138 @@
+"""Parity of the tcgen05 contraction kernel (GEMM / 3x3x3 conv / ConvTranspose) against fp32 torch ops that
+restate the reference's layers (nn.Linear, Conv3d(bias=False), ConvTranspose3d(k=s)) on bf16-rounded operands.
+bf16 x bf16 products are exact in fp32, so the only differences are accumulation order and the bf16 rounding of
+the stored output: tolerance 2^-8 relative to the output scale for bf16 outputs, 1e-4 for fp32 outputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _ops():
+    from hybrid_ctunet_b200 import ops
+    return ops
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def _maxrel(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("M,K,N,bn", [(432, 768, 2304, 128), (128, 64, 64, 64), (1000, 3072, 768, 128),
+                                      (3456, 96, 512, 128), (4096, 32, 64, 64), (864, 2048, 768, 64),
+                                      (300, 256, 256, 256), (260, 128, 32, 32)])
+def test_linear_bf16(M, K, N, bn):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5)
+    pw = ops.pack_matrix(w, block_n=bn)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, pw, out, dims=(M, 1, 1, 1))
+    ref = a.float() @ w.to(torch.bfloat16).float().t()
+    assert torch.isfinite(out.float()).all()
+    assert _maxrel(out.float(), ref) < 2 ** -7
+    assert _rel(out.float(), ref) < 2 ** -8
+
+
+def test_linear_bias_gelu_residual_f32_inplace():
+    ops = _ops()
+    M, K, N = 864, 768, 768
+    g = torch.Generator(device="cuda").manual_seed(7)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g)
+    pw = ops.pack_matrix(w, bias=b)
+    ref = x + F.linear(a.float(), w.to(torch.bfloat16).float(), b)
+    xx = x.clone()
+    ops.gemm(a, pw, xx, dims=(M, 1, 1, 1), out_mode=ops.OUT_F32, residual=xx)
+    assert _maxrel(xx, ref) < 1e-4
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, pw, out, dims=(M, 1, 1, 1), act=ops.ACT_GELU)
+    ref2 = F.gelu(F.linear(a.float(), w.to(torch.bfloat16).float(), b))
+    assert _maxrel(out.float(), ref2) < 2 ** -7
+
+
+def test_head_channel_first_f32():
+    ops = _ops()
+    B, X, Y, Z, Cin, Cout = 2, 8, 12, 16, 64, 14
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(B, X, Y, Z, Cin, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(Cout, Cin, device="cuda", generator=g) / 8
+    b = torch.randn(Cout, device="cuda", generator=g)
+    pw = ops.pack_matrix(w, bias=b)
+    out = torch.full((B, Cout, X, Y, Z), float("nan"), device="cuda")
+    ops.gemm(a, pw, out, dims=(X * Y * Z, 1, 1, B), out_mode=ops.OUT_F32_CF)
+    ref = F.conv3d(a.float().permute(0, 4, 1, 2, 3), w.to(torch.bfloat16).float()[:, :, None, None, None], b)
+    assert _maxrel(out, ref) < 1e-4
+
+
+def _pack_conv3(w):  # [Cout, Cin, kX, kY, kZ] -> [Cout, 27*Cin] (tap-major, channel-minor)
+    return w.permute(0, 2, 3, 4, 1).reshape(w.shape[0], -1)
+
+
+@pytest.mark.parametrize("B,X,Y,Z,Cin,Cout,bn", [(1, 8, 8, 32, 64, 64, 64), (2, 6, 6, 12, 128, 128, 128),
+                                                  (1, 12, 12, 24, 64, 128, 64), (1, 24, 24, 48, 128, 64, 64),
+                                                  (1, 5, 7, 9, 64, 64, 64), (1, 96, 96, 96, 64, 64, 64)])
+def test_conv3x3x3(B, X, Y, Z, Cin, Cout, bn):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(X * Y + Cin)
+    a = torch.randn(B, X, Y, Z, Cin, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(Cout, Cin, 3, 3, 3, device="cuda", generator=g) / (27 * Cin) ** 0.5
+    pw = ops.pack_matrix(_pack_conv3(w), ksize=3, a_c=Cin, block_n=bn)
+    out = torch.full((B, X, Y, Z, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    stats = torch.zeros(B, Cout, 2, device="cuda", dtype=torch.float64)
+    ops.gemm(a, pw, out, dims=(Z, Y, X, B), stats=stats)
+    ref = F.conv3d(a.float().permute(0, 4, 1, 2, 3), w.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 4, 1)
+    assert torch.isfinite(out.float()).all()
+    assert _maxrel(out.float(), ref) < 2 ** -7
+    assert _rel(out.float(), ref) < 2 ** -8
+    # fused InstanceNorm statistics are the sums of the stored (bf16) values
+    o = out.double().reshape(B, -1, Cout)
+    assert torch.allclose(stats[..., 0], o.sum(1), rtol=1e-6, atol=1e-3)
+    assert torch.allclose(stats[..., 1], (o * o).sum(1), rtol=1e-6, atol=1e-3)
+
+
+@pytest.mark.parametrize("B,X,Y,Z,Cin,Cout,u", [(1, 6, 6, 12, 128, 64, (2, 2, 2)), (2, 4, 6, 8, 128, 64, (2, 2, 1)),
+                                                (1, 6, 6, 12, 1024, 512, (2, 2, 2))])
+def test_conv_transpose_k_eq_s(B, X, Y, Z, Cin, Cout, u):
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(Cin + Cout)
+    a = torch.randn(B, X, Y, Z, Cin, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(Cin, Cout, *u, device="cuda", generator=g) / Cin ** 0.5
+    ux, uy, uz = u
+    w2 = w.permute(2, 3, 4, 1, 0).reshape(ux * uy * uz * Cout, Cin)
+    pw = ops.pack_matrix(w2, block_n=64, convt=(Cout, uz, uy, ux))
+    out = torch.full((B, X * ux, Y * uy, Z * uz, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, pw, out, dims=(Z, Y, X, B))
+    ref = F.conv_transpose3d(a.float().permute(0, 4, 1, 2, 3), w.to(torch.bfloat16).float(), stride=u)
+    ref = ref.permute(0, 2, 3, 4, 1)
+    assert torch.isfinite(out.float()).all()
+    assert _maxrel(out.float(), ref) < 2 ** -7
+
+
+def test_concat_by_offset_and_strided_input():
+    ops = _ops()
+    M, K, N = 512, 64, 64
+    g = torch.Generator(device="cuda").manual_seed(11)
+    big = torch.randn(M, 128, device="cuda", generator=g).to(torch.bfloat16)
+    a = big[:, 64:]  # row stride 128, channel offset 64
+    w = torch.randn(N, K, device="cuda", generator=g) / 8
+    pw = ops.pack_matrix(w)
+    out = torch.zeros(M, 128, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, pw, out, dims=(M, 1, 1, 1), out_col0=64)
+    ref = a.float() @ w.to(torch.bfloat16).float().t()
+    assert _maxrel(out[:, 64:].float(), ref) < 2 ** -7
+    assert (out[:, :64] == 0).all()
