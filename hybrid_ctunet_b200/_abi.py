@@ -1,15 +1,25 @@
 """argtypes/restype declarations for the non-GEMM entry points of include/ctunet_b200.h."""
 import ctypes as C
 
-_SIGS = {}
+P, I, L, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
-
-def sig(name, *argtypes):
-    _SIGS[name] = argtypes
+SIGS = {
+    "ctu_in_stats": (P, I, I, L, I, P, I, P),
+    "ctu_in_apply": (P, I, P, I, P, I, P, I, P, I, I, L, I, F, I, F, P),
+    "ctu_layernorm": (P, I, L, P, P, P, L, P, I, L, L, I, F, P),
+    "ctu_patchify_ln": (P, I, I, I, I, I, P, P, P, F, P),
+    "ctu_pwa_fuse": (P, P, P, L, I, I, P),
+    "ctu_subsample": (P, I, I, I, I, P, I, I, I, I, I, I, P),
+    "ctu_attention": (P, I, I, I, P, I, P, I, I, I, I, I, I, I, I, P),
+    "ctu_conv_cin1": (P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, I, I, P),
+    "ctu_blend_accumulate": (P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P),
+    "ctu_blend_count": (P, P, I, I, I, I, I, I, I, I, I, P),
+    "ctu_blend_normalize": (P, P, P, I, L, P),
+}
 
 
 def declare(lib):
-    for name, argtypes in _SIGS.items():
+    for name, argtypes in SIGS.items():
         fn = getattr(lib, name)
         fn.argtypes = list(argtypes)
         fn.restype = C.c_int

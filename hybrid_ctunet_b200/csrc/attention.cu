@@ -1,0 +1,228 @@
+// Fused softmax(Q K^T * scale + bias) V for the short sequences of the CTUNet path (sm_100a):
+//   - ViT MHSA, 432 tokens, 12 heads x 64                       (vit.py:66-78)
+//   - MultiAxisAttention, 216-token 6x6x6 windows, dim/32 heads x 32, block or grid partition, additive
+//     relative-position bias                                     (hybrid_CTUNet.py:481-511, 559-567)
+// These are <1 % of the path's FLOPs and far too short for a TMEM pipeline, so they run flash-style on
+// mma.sync m16n8k16 (bf16 in, fp32 accumulate) with the whole K/V of one (window, head) resident in shared
+// memory.  The window / grid partition of the reference's einops rearranges is folded into the row gather,
+// so activations never leave their natural channels-last order.
+#include "common.cuh"
+#include "../../include/ctunet_b200.h"
+#include "host_util.h"
+
+namespace ctu {
+
+struct TokenMap {
+  int mode;           // 0: rows = win*n + p; 1: block partition '(h h1)'; 2: grid partition '(h1 h)'
+  int X, Y, Z;        // token grid of one batch item
+  int nwx, nwy, nwz;  // windows per axis
+  int w;              // window edge (6)
+};
+
+__device__ __forceinline__ long long token_row(const TokenMap& m, int win, int p, int n) {
+  if (m.mode == 0) return (long long)win * n + p;
+  const int wz = win % m.nwz;
+  int t = win / m.nwz;
+  const int wy = t % m.nwy;
+  t /= m.nwy;
+  const int wx = t % m.nwx;
+  const int b = t / m.nwx;
+  const int pz = p % m.w;
+  const int py = (p / m.w) % m.w;
+  const int px = p / (m.w * m.w);
+  int x, y, z;
+  if (m.mode == 1) {
+    x = wx * m.w + px; y = wy * m.w + py; z = wz * m.w + pz;
+  } else {
+    x = px * m.nwx + wx; y = py * m.nwy + wy; z = pz * m.nwz + wz;
+  }
+  return (((long long)b * m.X + x) * m.Y + y) * m.Z + z;
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int KCHUNK = 48;  // keys per online-softmax step (3 k-tiles of 16)
+
+template <int D>
+__global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, int C,
+                                                        __nv_bfloat16* __restrict__ out, int ldo,
+                                                        const float* __restrict__ bias, float scale, int n, int n_pad,
+                                                        TokenMap map) {
+  constexpr int LDK = D + 8;
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_att);  // [n_pad][LDK]
+  const int LDV = n_pad + 8;
+  __nv_bfloat16* Vt = Ks + (size_t)n_pad * LDK;                     // [D][LDV]
+
+  const int qt = blockIdx.x, h = blockIdx.y, win = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  // ---- stage K (row-major) and V (transposed) of this (window, head)
+  constexpr int VPR = D / 8;
+  for (int i = tid; i < n_pad * VPR; i += 128) {
+    const int j = i / VPR, vi = i % VPR;
+    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    if (j < n) {
+      const __nv_bfloat16* rp = qkv + token_row(map, win, j, n) * ld_qkv + h * D + vi * 8;
+      kv = *reinterpret_cast<const uint4*>(rp + C);
+      vv = *reinterpret_cast<const uint4*>(rp + 2 * C);
+    }
+    *reinterpret_cast<uint4*>(Ks + (size_t)j * LDK + vi * 8) = kv;
+    const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) Vt[(size_t)(vi * 8 + e) * LDV + j] = ve[e];
+  }
+
+  // ---- Q fragments (A operand) straight from global memory
+  const int q0 = qt * 64 + warp * 16;
+  const int qa = q0 + g, qb = q0 + g + 8;
+  const bool va = qa < n, vb = qb < n;
+  const long long ra = va ? token_row(map, win, qa, n) : 0;
+  const long long rb = vb ? token_row(map, win, qb, n) : 0;
+  uint32_t qf[D / 16][4];
+#pragma unroll
+  for (int kk = 0; kk < D / 16; ++kk) {
+    const int c = h * D + kk * 16 + 2 * t;
+    qf[kk][0] = va ? *reinterpret_cast<const uint32_t*>(qkv + ra * ld_qkv + c) : 0u;
+    qf[kk][1] = vb ? *reinterpret_cast<const uint32_t*>(qkv + rb * ld_qkv + c) : 0u;
+    qf[kk][2] = va ? *reinterpret_cast<const uint32_t*>(qkv + ra * ld_qkv + c + 8) : 0u;
+    qf[kk][3] = vb ? *reinterpret_cast<const uint32_t*>(qkv + rb * ld_qkv + c + 8) : 0u;
+  }
+  __syncthreads();
+
+  float o[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
+  const float LOG2E = 1.4426950408889634f;
+  const float sl = scale * LOG2E;
+  const float* bias_a = bias ? bias + ((long long)h * n + (va ? qa : 0)) * n : nullptr;
+  const float* bias_b = bias ? bias + ((long long)h * n + (vb ? qb : 0)) * n : nullptr;
+
+  for (int k0 = 0; k0 < n_pad; k0 += KCHUNK) {
+    float s[KCHUNK / 8][4];
+#pragma unroll
+    for (int j = 0; j < KCHUNK / 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      const __nv_bfloat16* kp = Ks + (size_t)(k0 + j * 8 + g) * LDK + 2 * t;
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kp + kk * 16);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kp + kk * 16 + 8);
+        mma_bf16_16816(s[j], qf[kk], b0, b1);
+      }
+    }
+    // scale (+bias), mask, running max
+    float mx_a = -INFINITY, mx_b = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < KCHUNK / 8; ++j) {
+      const int key = k0 + j * 8 + 2 * t;
+      float ba0 = 0.f, ba1 = 0.f, bb0 = 0.f, bb1 = 0.f;
+      if (bias != nullptr && key < n) {
+        const float2 x = *reinterpret_cast<const float2*>(bias_a + key);
+        const float2 y = *reinterpret_cast<const float2*>(bias_b + key);
+        ba0 = x.x * LOG2E; ba1 = x.y * LOG2E; bb0 = y.x * LOG2E; bb1 = y.y * LOG2E;
+      }
+      s[j][0] = key < n ? fmaf(s[j][0], sl, ba0) : -INFINITY;
+      s[j][1] = key + 1 < n ? fmaf(s[j][1], sl, ba1) : -INFINITY;
+      s[j][2] = key < n ? fmaf(s[j][2], sl, bb0) : -INFINITY;
+      s[j][3] = key + 1 < n ? fmaf(s[j][3], sl, bb1) : -INFINITY;
+      mx_a = fmaxf(mx_a, fmaxf(s[j][0], s[j][1]));
+      mx_b = fmaxf(mx_b, fmaxf(s[j][2], s[j][3]));
+    }
+    mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1));
+    mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
+    mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
+    mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
+    const float mn_a = fmaxf(m_a, mx_a), mn_b = fmaxf(m_b, mx_b);  // finite: chunk 0 always holds valid keys
+    const float ca = exp2f(m_a - mn_a), cb = exp2f(m_b - mn_b);
+    m_a = mn_a; m_b = mn_b;
+    l_a *= ca; l_b *= cb;
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) { o[i][0] *= ca; o[i][1] *= ca; o[i][2] *= cb; o[i][3] *= cb; }
+    uint32_t pf[KCHUNK / 16][4];
+#pragma unroll
+    for (int j = 0; j < KCHUNK / 8; ++j) {
+      const float p0 = exp2f(s[j][0] - mn_a), p1 = exp2f(s[j][1] - mn_a);
+      const float p2 = exp2f(s[j][2] - mn_b), p3 = exp2f(s[j][3] - mn_b);
+      l_a += p0 + p1; l_b += p2 + p3;
+      // C fragments of key tiles (2kt, 2kt+1) are the A fragment of k-tile kt
+      pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+#pragma unroll
+    for (int kt = 0; kt < KCHUNK / 16; ++kt) {
+#pragma unroll
+      for (int dn = 0; dn < D / 8; ++dn) {
+        const __nv_bfloat16* vp = Vt + (size_t)(dn * 8 + g) * LDV + k0 + kt * 16 + 2 * t;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vp);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vp + 8);
+        mma_bf16_16816(o[dn], pf[kt], b0, b1);
+      }
+    }
+  }
+  l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
+  l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
+  l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);
+  l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
+  const float ia = 1.f / l_a, ib = 1.f / l_b;
+#pragma unroll
+  for (int dn = 0; dn < D / 8; ++dn) {
+    const int c = h * D + dn * 8 + 2 * t;
+    if (va) *reinterpret_cast<uint32_t*>(out + ra * ldo + c) = pack_bf16x2(o[dn][0] * ia, o[dn][1] * ia);
+    if (vb) *reinterpret_cast<uint32_t*>(out + rb * ldo + c) = pack_bf16x2(o[dn][2] * ib, o[dn][3] * ib);
+  }
+}
+
+}  // namespace ctu
+
+using namespace ctu;
+
+// qkv: bf16 [rows][ld_qkv] with q|k|v thirds of width C = heads*dim_head; out: bf16 [rows][ldo].
+// mode 0: `windows` consecutive groups of n rows (ViT: windows = batch, n = 432).
+// mode 1/2: block / grid partition of a [batch, X, Y, Z] token grid into w^3 windows (n = w^3).
+// bias: fp32 [heads][n][n] added to the scaled scores, or NULL.
+extern "C" int ctu_attention(const void* qkv, int ld_qkv, int C, int dim_head, void* out, int ldo, const float* bias,
+                             int n, int windows, int mode, int batch, int X, int Y, int Z, int w, void* stream) {
+  if (!qkv || !out || (dim_head != 32 && dim_head != 64) || C % dim_head || ld_qkv % 8 || ldo % 2) return CTU_E_BADARG;
+  TokenMap m;
+  m.mode = mode; m.X = X; m.Y = Y; m.Z = Z; m.w = w;
+  m.nwx = m.nwy = m.nwz = 1;
+  if (mode != 0) {
+    if (w <= 0 || X % w || Y % w || Z % w || n != w * w * w) return CTU_E_BADARG;
+    m.nwx = X / w; m.nwy = Y / w; m.nwz = Z / w;
+    windows = batch * m.nwx * m.nwy * m.nwz;
+  }
+  if (bias && (n % 2)) return CTU_E_BADARG;
+  const int n_pad = (n + KCHUNK - 1) / KCHUNK * KCHUNK;
+  const int heads = C / dim_head;
+  const size_t smem = ((size_t)n_pad * (dim_head + 8) + (size_t)dim_head * (n_pad + 8)) * 2;
+  dim3 grid((n + 63) / 64, heads, windows);
+  const float scale = 1.0f / sqrtf((float)dim_head);
+  cudaStream_t st = (cudaStream_t)stream;
+  constexpr int kMaxSmem = 160 * 1024;
+  if (smem > (size_t)kMaxSmem) return CTU_E_UNSUPPORTED;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  if (dim_head == 64) {
+    attention_kernel<64><<<grid, 128, smem, st>>>((const __nv_bfloat16*)qkv, ld_qkv, C, (__nv_bfloat16*)out, ldo, bias,
+                                                  scale, n, n_pad, m);
+  } else {
+    attention_kernel<32><<<grid, 128, smem, st>>>((const __nv_bfloat16*)qkv, ld_qkv, C, (__nv_bfloat16*)out, ldo, bias,
+                                                  scale, n, n_pad, m);
+  }
+  count_launch();
+  return (int)cudaGetLastError();
+}
