@@ -40,7 +40,7 @@ class WeightCache:
         self._cache: Dict[str, Tuple[tuple, object]] = {}
 
     def _get(self, key: str, names, build):
-        ps = [self.params[n] for n in names]
+        ps = [self.params[n.lstrip('.')] for n in names]
         tag = tuple((p.data_ptr(), p._version, str(p.device)) for p in ps)
         hit = self._cache.get(key)
         if hit is not None and hit[0] == tag:
@@ -349,17 +349,19 @@ class Engine:
         fused = self.pixelweight_attention(pre + ".pixelweight_attention2", up, skip)
         return self.res_block(pre + ".up_addconv_block2", fused, cout, cout)
 
-    def window_attention(self, pre: str, x, grid, mode: int):
-        """Residual(MultiAxisAttention) (hybrid_CTUNet.py:481-511); x: [T, D] residual stream, updated in place."""
+    def window_attention(self, pre: str, x, grid, mode: int, out=None):
+        """Residual(MultiAxisAttention) (hybrid_CTUNet.py:481-511); x: [T, D] residual stream, updated in place
+        unless `out` is given."""
         T, D = x.shape
+        out = x if out is None else out
         h = self._empty(T, D)
         ops.layernorm(x, self.w.f32(pre + ".norm.weight"), self.w.f32(pre + ".norm.bias"), h)
         qkv = self._empty(T, 3 * D)
         ops.gemm(h, self.w.linear(pre + ".to_qkv", bias=False), qkv, dims=(T, 1, 1, 1))
         ops.attention(qkv, h, dim_head=32, n=216, mode=mode, bias=self.w.rel_bias(pre + ".rel_pos_bias"), grid=grid, w=6)
-        ops.gemm(h, self.w.linear(pre + ".to_out.0", bias=False), x, dims=(T, 1, 1, 1),
-                 out_mode=OUT_F32 if x.dtype == torch.float32 else OUT_BF16, residual=x)
-        return x
+        ops.gemm(h, self.w.linear(pre + ".to_out.0", bias=False), out, dims=(T, 1, 1, 1),
+                 out_mode=OUT_F32 if out.dtype == torch.float32 else OUT_BF16, residual=x)
+        return out
 
     def up_attention_block(self, pre: str, tokens, B: int, grid0, out_last=None):
         """UpAttentionBlock (hybrid_CTUNet.py:554-591); tokens: [B*X*Y*Z, 768] in (x,y,z) order = proj_feat view.
@@ -372,14 +374,17 @@ class Engine:
             f = DS_STRIDE[::-1][ind]
             T, D = x.shape
             xb = self._empty(T, D)  # bf16 stage output feeding the pixel-shuffle GEMM
+            # the stage input is also a returned feature map (or the caller's tokens): the first residual update
+            # goes to a fresh buffer, later ones are in place
+            fresh = self._empty(T, D, dtype=x.dtype)
             if ind <= 2:
-                self.window_attention(p + ".1.fn", x, (B, X, Y, Z), 1)
+                x = self.window_attention(p + ".1.fn", x, (B, X, Y, Z), 1, out=fresh)
                 self.ffn(p + ".2.fn", x)
                 self.window_attention(p + ".5.fn", x, (B, X, Y, Z), 2)
                 self.ffn(p + ".6.fn", x, out=xb)
                 ps = self.w.pixel_shuffle(p + ".8.to_out", f)
             else:
-                self.ffn(p + ".1.fn", x)
+                x = self.ffn(p + ".1.fn", x, out=fresh)
                 self.ffn(p + ".2.fn", x, out=xb)
                 ps = self.w.pixel_shuffle(p + ".4.to_out", f)
             out = out_last if (ind == 3 and out_last is not None) else None
@@ -427,7 +432,7 @@ class Engine:
         B, X, Y, Z, _ = skip.shape
         cat = self._empty(B, X, Y, Z, 2 * cout)
         self.up_gemm(inp, self.w.convt(pre + ".transp_conv.conv"), out=cat[..., :cout])
-        cat[..., cout:].copy_(skip)
+        ops.subsample(skip, cat[..., cout:], (1, 1, 1))  # stride-1 gather == strided copy into the concat buffer
         return self.res_block(pre + ".conv_block", cat, 2 * cout, cout)
 
     def cunet(self, x_in, layers):
