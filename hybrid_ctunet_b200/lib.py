@@ -11,6 +11,7 @@ import os
 from . import build as _build
 
 _LIB = None
+_DEVICE_OK = False
 
 
 class CtuError(RuntimeError):
@@ -94,7 +95,10 @@ def launch_count() -> int:
 
 def require_device():
     """Fail loudly unless the CUDA library is loaded and the current device is a B200-class (sm_100) GPU."""
+    global _DEVICE_OK
     lib = load()
-    if not lib.ctu_device_ok():
-        raise CtuError("ctunet_b200 needs an sm_100 (B200) GPU; there is no CPU fallback")
+    if not _DEVICE_OK:  # cudaGetDeviceProperties is slow: query once
+        if not lib.ctu_device_ok():
+            raise CtuError("ctunet_b200 needs an sm_100 (B200) GPU; there is no CPU fallback")
+        _DEVICE_OK = True
     return lib

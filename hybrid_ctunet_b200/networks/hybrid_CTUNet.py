@@ -290,9 +290,41 @@ class _Net(KernelModule):
     def _run(self, eng, x):
         raise NotImplementedError
 
+    def enable_cuda_graph(self, flag: bool = True):
+        """Replay the whole forward as one CUDA graph per input shape (inference only).  The returned logits are
+        the graph's static output buffers: consume them before the next call (sliding-window blending does)."""
+        object.__setattr__(self, "_use_graph", bool(flag))
+        object.__setattr__(self, "_graphs", {})
+        return self
+
+    def _graph_forward(self, eng, x):
+        graphs = getattr(self, "_graphs", None)
+        if graphs is None:
+            graphs = {}
+            object.__setattr__(self, "_graphs", graphs)
+        tag = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = tuple(x.shape)
+        ent = graphs.get(key)
+        if ent is not None and ent["tag"] != tag:  # weights changed: packed copies inside the graph are stale
+            ent = None
+        if ent is None:
+            static_x = x.clone()
+            self._run(eng, static_x)  # warm-up: packs weights, sets kernel attributes, primes the allocator
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._run(eng, static_x)
+            ent = dict(graph=g, x=static_x, out=out, tag=tag)
+            graphs[key] = ent
+        ent["x"].copy_(x)
+        ent["graph"].replay()
+        return ent["out"]
+
     def forward(self, x_in):
         x = self._input(x_in)
         eng = self._engine()
+        if getattr(self, "_use_graph", False):
+            return self._graph_forward(eng, x)
         return self._run(eng, x)
 
 

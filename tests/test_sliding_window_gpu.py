@@ -1,0 +1,82 @@
+"""Sliding-window inference on the CUDA blend kernels against the reference restatement
+(oracle/sliding_window_oracle.py follows trainer_CTUNet.py:417-557 / trainer_CUNet.py:268-400 literally, run here
+with torch ops on the same device).  With the same predictor the blended volume must be BIT-EXACT: window order,
+importance map, separate multiply / add roundings and the final divide all match."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _pred2(n_cls=14):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(1, n_cls, 1, 1, 1, device="cuda", generator=g)
+    b = torch.randn(1, n_cls, 1, 1, 1, device="cuda", generator=g)
+
+    def predictor(w):
+        h0 = torch.sin(w * 3.0) * a + b
+        h1 = torch.cos(w * 2.0) * b - a
+        return ((h0, h0[:, :, ::2, ::2], h0[:, :, ::4, ::4]), (h1, h1 + 1))
+    return predictor
+
+
+@pytest.mark.parametrize("shape,roi,overlap,mode", [((1, 1, 70, 50, 45), (32, 32, 32), 0.5, "gaussian"),
+                                                    ((2, 1, 64, 64, 64), (32, 32, 32), 0.5, "gaussian"),
+                                                    ((1, 1, 40, 33, 37), (16, 16, 16), 0.7, "gaussian"),
+                                                    ((1, 1, 50, 50, 50), (32, 32, 32), 0.25, "constant"),
+                                                    ((1, 1, 20, 40, 24), (32, 32, 32), 0.5, "gaussian")])
+def test_two_head_blend_bit_exact(shape, roi, overlap, mode):
+    from hybrid_ctunet_b200.trainer_CTUNet import sliding_window_inference
+    from oracle import sliding_window_oracle as O
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    x = torch.rand(*shape, device="cuda", generator=g)
+    pred = _pred2()
+    a0, a1 = sliding_window_inference(x, roi, 4, pred, overlap=overlap, mode=mode)
+    r0, r1 = O.sliding_window_inference(x, roi, 4, pred, overlap=overlap, mode=mode, two_heads=True)
+    assert a0.shape == r0.shape == (shape[0], 14) + tuple(shape[2:])
+    assert torch.equal(a0, r0) and torch.equal(a1, r1)
+
+
+def test_one_head_blend_bit_exact():
+    from hybrid_ctunet_b200.trainer_CUNet import sliding_window_inference
+    from oracle import sliding_window_oracle as O
+    g = torch.Generator(device="cuda").manual_seed(77)
+    x = torch.rand(1, 1, 48, 80, 40, device="cuda", generator=g)
+    pred2 = _pred2()
+    pred = lambda w: pred2(w)[0]
+    a = sliding_window_inference(x, (32, 32, 32), 4, pred, overlap=0.5, mode="gaussian")
+    r = O.sliding_window_inference(x, (32, 32, 32), 4, pred, overlap=0.5, mode="gaussian", two_heads=False)
+    assert torch.equal(a, r)
+
+
+def test_full_window_and_overlap_errors():
+    from hybrid_ctunet_b200.trainer_CTUNet import sliding_window_inference
+    x = torch.rand(1, 1, 32, 32, 32, device="cuda")
+    pred = _pred2()
+    a0, _ = sliding_window_inference(x, (32, 32, 32), 4, pred, overlap=0.5, mode="gaussian")
+    assert torch.allclose(a0, pred(x)[0][0], rtol=1e-6, atol=1e-6)  # one window: (imp*p)/imp
+    with pytest.raises(AssertionError):
+        sliding_window_inference(x, (32, 32, 32), 4, pred, overlap=1.0)
+
+
+def test_ctunet_sliding_window_three_windows():
+    """The real predictor: CTUNet(101, pf8) over a 96x96x144 volume (3 windows, overlap 0.5), eager vs CUDA-graph
+    replay vs the oracle blend of the same model's logits."""
+    from hybrid_ctunet_b200.networks.hybrid_CTUNet import CTUNet
+    from hybrid_ctunet_b200.trainer_CTUNet import sliding_window_inference
+    from oracle import sliding_window_oracle as O
+    torch.manual_seed(0)
+    m = CTUNet(in_channels=1, dim_conv_stem=64, out_channels=14, model_depth=101, img_size=(96, 96), frames=96,
+               patch_frame=8).cuda().eval()
+    torch.manual_seed(2)
+    x = torch.rand(1, 1, 96, 96, 144).cuda()
+    with torch.no_grad():
+        a0, a1 = sliding_window_inference(x, (96, 96, 96), 4, m, overlap=0.5, mode="gaussian")
+        r0, r1 = O.sliding_window_inference(x, (96, 96, 96), 4, m, overlap=0.5, mode="gaussian", two_heads=True)
+        m.enable_cuda_graph(True)
+        g0, g1 = sliding_window_inference(x, (96, 96, 96), 4, m, overlap=0.5, mode="gaussian")
+    assert a0.shape == (1, 14, 96, 96, 144) and torch.isfinite(a0).all() and torch.isfinite(a1).all()
+    rel = lambda u, v: ((u - v).norm() / v.norm()).item()
+    # the fp64 atomics of the InstanceNorm statistics make two runs of the model differ in the last bits only
+    assert rel(a0, r0) < 1e-3 and rel(a1, r1) < 1e-4
+    assert rel(g0, r0) < 1e-3 and rel(g1, r1) < 1e-4
