@@ -1,30 +1,36 @@
 // tcgen05 / TMEM / TMA contraction kernel for sm_100a: plain GEMM, 3x3x3 implicit-GEMM Conv3d and
-// kernel==stride ConvTranspose3d share one warp-specialised kernel (see include/ctunet_b200.h).
+// kernel==stride ConvTranspose3d share one persistent, warp-specialised kernel (see include/ctunet_b200.h).
 //
+// One CTA per SM loops over output tiles (128 voxels x BLOCK_N channels, N fastest so that CTAs running
+// concurrently share the activation rows in L2):
 //   warp 0 (1 lane) : TMA producer — per K block one 5-D box of activations (128 voxels x 64 channels, shifted
-//                     by the filter tap, out-of-range voxels zero-filled by the TMA unit = conv padding) and
-//                     one 2-D box of packed weights (BLOCK_N rows x 64).
-//   warp 1 (1 lane) : MMA issuer — 4 x tcgen05.mma (M128 x BLOCK_N x K16) per K block into a TMEM accumulator,
-//                     tcgen05.commit releases the smem stage / signals the epilogue.
-//   warps 2..5      : epilogue — tcgen05.ld the accumulator (one voxel row per thread), bias / GELU / residual,
-//                     InstanceNorm partial statistics (warp transpose-reduce + fp64 atomics), bf16/fp32 stores.
-// One output tile (128 x BLOCK_N) per CTA; several CTAs are co-resident per SM so one CTA's epilogue overlaps
-// another's main loop.
+//                     by the filter tap; out-of-range voxels are zero-filled by the TMA unit = conv padding) and
+//                     one 2-D box of packed weights (BLOCK_N x 64) into a STAGES-deep smem ring that runs ahead
+//                     across tile boundaries.
+//   warp 1 (1 lane) : MMA issuer — 4 x tcgen05.mma (M128 x BLOCK_N x K16) per K block into one of TWO TMEM
+//                     accumulators; tcgen05.commit frees the smem stage / publishes the accumulator.
+//   warps 2..5      : epilogue — tcgen05.ld (one voxel row per thread), bias / GELU / residual, InstanceNorm
+//                     partial statistics (warp transpose-reduce + fp64 atomics), then either a swizzled smem
+//                     staging tile written back with one TMA store per 64-channel slab (bf16 rows), or direct
+//                     stores (fp32 rows, channel-first heads, transposed-conv scatter).  The epilogue of tile i
+//                     overlaps the main loop of tile i+1 through the second accumulator.
 #include "common.cuh"
 #include "../../include/ctunet_b200.h"
 #include "host_util.h"
+#include <stdlib.h>
 
 namespace ctu {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int SLAB_BYTES = BLOCK_M * 128;  // 128 rows x 64 bf16
 
 struct GemmParams {
   int b1, b2, b3;
   int T1, T2, T3;
   int d1, d2, d3;
-  int n_tiles;
+  int n_tiles, total_tiles;
   int num_kb, cblocks, a_c;
   int k1, k2;
   int pad;
@@ -36,9 +42,44 @@ struct GemmParams {
   int n_real, out_mode, ldc, act, res_mode, ldr;
   int convt_cout, u1, u2, u3;
   int stats_ld, out_col0;
+  int tma_store;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+struct TileCoord {
+  int x1, x2, x3, t4, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, int bn) {
+  TileCoord c;
+  const int n_tile = tile % p.n_tiles;
+  int m_tile = tile / p.n_tiles;
+  const int t1 = m_tile % p.T1;
+  m_tile /= p.T1;
+  const int t2 = m_tile % p.T2;
+  m_tile /= p.T2;
+  const int t3 = m_tile % p.T3;
+  c.t4 = m_tile / p.T3;
+  c.x1 = t1 * p.b1;
+  c.x2 = t2 * p.b2;
+  c.x3 = t3 * p.b3;
+  c.n0 = n_tile * bn;
+  return c;
+}
+
+// Exact-form GELU 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7, far
+// below the bf16 rounding of the stored result): ~15 instructions instead of erff's ~50, the epilogue of the FFN
+// up-projections is otherwise bound by it.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
+  const float erf_v = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_v);
+}
 
 // Column sums over the 32 lanes of a warp for 32 per-lane values: after the call, lane L holds the sum of
 // v[L] over all lanes (31 shuffles instead of 160).
@@ -56,22 +97,29 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
   return v[0];
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                        const __grid_constant__ CUtensorMap tmB,
-                                                        const GemmParams p) {
+template <int BN, int STAGES, int OUT_BUFS, int CTAS_PER_SM>
+__global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB,
+                                                           const __grid_constant__ CUtensorMap tmC,
+                                                           const GemmParams p) {
   constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  constexpr int CH = BN < 32 ? BN : 32;  // columns per tcgen05.ld
+  constexpr int ACC_COLS = 2 * BN;
+  constexpr int TMEM_COLS = ACC_COLS < 32 ? 32 : ACC_COLS;  // 32, 64, 128, 256 or 512
+  constexpr int CH = BN < 32 ? BN : 32;                       // columns per tcgen05.ld
+  constexpr int SLABS = BN / 64;                              // 64-channel staging slabs (0: no TMA store path)
   constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, BN);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_STAGE_BYTES);
-  // bars[0..STAGES) full, [STAGES..2*STAGES) empty, [2*STAGES] accumulator ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint8_t* smem_b = smem_a + STAGES * A_STAGE_BYTES;
+  uint8_t* smem_c = smem_b + STAGES * B_STAGE_BYTES;  // [OUT_BUFS][SLABS][SLAB_BYTES], 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + OUT_BUFS * SLABS * SLAB_BYTES);
+  uint64_t* bar_full = bars;
+  uint64_t* bar_empty = bars + STAGES;
+  uint64_t* bar_tfull = bars + 2 * STAGES;
+  uint64_t* bar_tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float2* stat_scratch = reinterpret_cast<float2*>(tmem_slot + 2);  // [4][BN]
 
   const int warp = threadIdx.x >> 5;
@@ -80,11 +128,15 @@ __global__ void __launch_bounds__(192) umma_gemm_kernel(const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&bars[s]), 1);
-      mbar_init(smem_u32(&bars[STAGES + s]), 1);
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
     }
-    mbar_init(smem_u32(&bars[2 * STAGES]), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_tfull[s]), 1);
+      mbar_init(smem_u32(&bar_tempty[s]), 4);
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -96,194 +148,281 @@ __global__ void __launch_bounds__(192) umma_gemm_kernel(const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // tile decode
-  const int n_tile = blockIdx.x % p.n_tiles;
-  int m_tile = blockIdx.x / p.n_tiles;
-  const int t1 = m_tile % p.T1;
-  m_tile /= p.T1;
-  const int t2 = m_tile % p.T2;
-  m_tile /= p.T2;
-  const int t3 = m_tile % p.T3;
-  const int t4 = m_tile / p.T3;
-  const int x1 = t1 * p.b1, x2 = t2 * p.b2, x3 = t3 * p.b3;
-  const int n0 = n_tile * BN;
-
   if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(smem_u32(&bars[STAGES + s]), ph ^ 1);
-        const uint32_t full = smem_u32(&bars[s]);
-        mbar_expect_tx(full, A_STAGE_BYTES + B_STAGE_BYTES);
-        const int tap = kb / p.cblocks;
-        const int cb = kb - tap * p.cblocks;
-        const int f1 = tap % p.k1;
-        const int f2 = (tap / p.k1) % p.k2;
-        const int f3 = tap / (p.k1 * p.k2);
-        tma_load_5d(smem_u32(smem_a + s * A_STAGE_BYTES), &tmA, full, cb * BLOCK_K, x1 + f1 - p.pad,
-                    x2 + f2 - p.pad, x3 + f3 - p.pad, t4);
-        tma_load_2d(smem_u32(smem_b + s * B_STAGE_BYTES), &tmB, full, tap * p.a_c + cb * BLOCK_K, n0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile, BN);
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+          const uint32_t full = smem_u32(&bar_full[s]);
+          mbar_expect_tx(full, A_STAGE_BYTES + B_STAGE_BYTES);
+          const int tap = kb / p.cblocks;
+          const int cb = kb - tap * p.cblocks;
+          const int f1 = tap % p.k1;
+          const int f2 = (tap / p.k1) % p.k2;
+          const int f3 = tap / (p.k1 * p.k2);
+          tma_load_5d(smem_u32(smem_a + s * A_STAGE_BYTES), &tmA, full, cb * BLOCK_K, tc.x1 + f1 - p.pad,
+                      tc.x2 + f2 - p.pad, tc.x3 + f3 - p.pad, tc.t4);
+          tma_load_2d(smem_u32(smem_b + s * B_STAGE_BYTES), &tmB, full, tap * p.a_c + cb * BLOCK_K, tc.n0);
+        }
       }
     }
   } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(smem_u32(&bars[s]), ph);
+      uint32_t it = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        const int slot = lt & 1;
+        const uint32_t uph = (lt >> 1) & 1;
+        mbar_wait(smem_u32(&bar_tempty[slot]), uph ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + s * A_STAGE_BYTES));
-        const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + s * B_STAGE_BYTES));
+        const uint32_t acc = tmem_base + (uint32_t)(slot * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(smem_u32(&bar_full[s]), ph);
+          tc_fence_after();
+          const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + s * A_STAGE_BYTES));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + s * B_STAGE_BYTES));
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) {
-          // advance 16 bf16 = 32 bytes inside the 128-byte swizzled row: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzled row: +2 in the (addr >> 4) field
+            umma_bf16(acc, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&bar_empty[s]));
         }
-        umma_commit(smem_u32(&bars[STAGES + s]));
+        umma_commit(smem_u32(&bar_tfull[slot]));
       }
-      umma_commit(smem_u32(&bars[2 * STAGES]));
     }
   } else {
-    // ------------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------------ epilogue (warps 2..5, 128 threads)
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;
+    const int e = threadIdx.x - 64;
     const int i1 = r % p.b1;
     const int i2 = (r / p.b1) % p.b2;
     const int i3 = r / (p.b1 * p.b2);
-    const int v1 = x1 + i1, v2 = x2 + i2, v3 = x3 + i3;
-    const bool valid = (v1 < p.d1) && (v2 < p.d2) && (v3 < p.d3);
-
-    int a1 = 0, a2 = 0, a3 = 0, colbase = n0;
-    if (p.convt_cout > 0) {
-      const int sub = n0 / p.convt_cout;
-      colbase = n0 - sub * p.convt_cout;
-      a1 = sub % p.u1;
-      a2 = (sub / p.u1) % p.u2;
-      a3 = sub / (p.u1 * p.u2);
-    }
+    const bool use_tma = (SLABS > 0) && (p.tma_store != 0);
+    const bool sync_tiles = use_tma || (p.stats != nullptr);
     const long long o1 = (long long)p.d1 * p.u1, o2 = (long long)p.d2 * p.u2, o3 = (long long)p.d3 * p.u3;
-    const long long out_row = ((t4 * o3 + (long long)v3 * p.u3 + a3) * o2 + ((long long)v2 * p.u2 + a2)) * o1 +
-                              ((long long)v1 * p.u1 + a1);
 
-    mbar_wait(smem_u32(&bars[2 * STAGES]), 0);
-    tc_fence_after();
+    constexpr int STAT_PER_THREAD = (BN + 127) / 128;
+    float acc_s[STAT_PER_THREAD], acc_q[STAT_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < STAT_PER_THREAD; ++k) acc_s[k] = acc_q[k] = 0.f;
+    int stat_batch = -1;
+    const int n0_cta = (blockIdx.x % p.n_tiles) * BN;
+    auto flush_stats = [&](int b) {
+      if (b < 0) return;
+#pragma unroll
+      for (int k = 0; k < STAT_PER_THREAD; ++k) {
+        const int c = e + 128 * k;
+        if (c < BN && n0_cta + c < p.n_real) {
+          double* dst = p.stats + ((long long)b * p.stats_ld + n0_cta + c) * 2;
+          atomicAdd(dst, (double)acc_s[k]);
+          atomicAdd(dst + 1, (double)acc_q[k]);
+        }
+        acc_s[k] = acc_q[k] = 0.f;
+      }
+    };
+
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const int slot = lt & 1;
+      const uint32_t uph = (lt >> 1) & 1;
+      const TileCoord tc = decode_tile(p, tile, BN);
+      const int n0 = tc.n0;
+      const int v1 = tc.x1 + i1, v2 = tc.x2 + i2, v3 = tc.x3 + i3;
+      const bool valid = (v1 < p.d1) && (v2 < p.d2) && (v3 < p.d3);
+      int a1 = 0, a2 = 0, a3 = 0, colbase = n0;
+      if (p.convt_cout > 0) {
+        const int sub = n0 / p.convt_cout;
+        colbase = n0 - sub * p.convt_cout;
+        a1 = sub % p.u1;
+        a2 = (sub / p.u1) % p.u2;
+        a3 = sub / (p.u1 * p.u2);
+      }
+      const long long out_row = ((tc.t4 * o3 + (long long)v3 * p.u3 + a3) * o2 + ((long long)v2 * p.u2 + a2)) * o1 +
+                                ((long long)v1 * p.u1 + a1);
+      uint8_t* cbuf = smem_c + (size_t)(OUT_BUFS > 0 ? (lt % (OUT_BUFS > 0 ? OUT_BUFS : 1)) : 0) * SLABS * SLAB_BYTES;
+
+      mbar_wait(smem_u32(&bar_tfull[slot]), uph);
+      tc_fence_after();
+      if (sync_tiles) {
+        // the staging buffer about to be overwritten must have been read by its TMA store (OUT_BUFS tiles ago),
+        // and every thread must be done with the previous tile's statistics scratch
+        if (use_tma && e == 0) {
+          if (OUT_BUFS > 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        named_bar_sync(1, 128);
+      }
 
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += CH) {
-      uint32_t raw[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      if constexpr (CH == 32) tmem_ld32(taddr, raw);
-      else tmem_ld16(taddr, raw);
-      tmem_ld_wait();
-      float v[32];
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        uint32_t raw[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN + c0);
+        if constexpr (CH == 32) tmem_ld32(taddr, raw);
+        else tmem_ld16(taddr, raw);
+        tmem_ld_wait();
+        float v[32];
 #pragma unroll
-      for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(raw[j]);
+        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(raw[j]);
 #pragma unroll
-      for (int j = CH; j < 32; ++j) v[j] = 0.f;
+        for (int j = CH; j < 32; ++j) v[j] = 0.f;
 
-      const int gcol = n0 + c0;  // column in the GEMM's N space (bias / stats / n_real)
-      if (p.bias != nullptr) {
-#pragma unroll
-        for (int j = 0; j < CH; ++j)
-          if (gcol + j < p.n_real) v[j] += __ldg(p.bias + gcol + j);
-      }
-      if (p.act == CTU_ACT_GELU) {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
-      }
-      const int ocol = p.out_col0 + colbase + c0;  // column inside an output row
-      if (p.res_mode == CTU_RES_F32 && valid) {
-        const float* rp = reinterpret_cast<const float*>(p.residual) + out_row * p.ldr + ocol;
-#pragma unroll
-        for (int j = 0; j < CH; j += 4) {
-          if (gcol + j < p.n_real) {
-            const float4 rv = *reinterpret_cast<const float4*>(rp + j);
-            v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
-          }
-        }
-      } else if (p.res_mode == CTU_RES_BF16 && valid) {
-        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + out_row * p.ldr + ocol;
-#pragma unroll
-        for (int j = 0; j < CH; j += 8) {
-          if (gcol + j < p.n_real) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(rp + j);
-            float2 f;
-            f = unpack_bf16x2(rv.x); v[j] += f.x; v[j + 1] += f.y;
-            f = unpack_bf16x2(rv.y); v[j + 2] += f.x; v[j + 3] += f.y;
-            f = unpack_bf16x2(rv.z); v[j + 4] += f.x; v[j + 5] += f.y;
-            f = unpack_bf16x2(rv.w); v[j + 6] += f.x; v[j + 7] += f.y;
-          }
-        }
-      }
-
-      if (p.out_mode == CTU_OUT_BF16_ROWS) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-        if (valid) {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldc + ocol;
-#pragma unroll
-          for (int j = 0; j < CH; j += 8) {
-            if (gcol + j < p.n_real)
-              *reinterpret_cast<uint4*>(op + j) = make_uint4(pk[j / 2], pk[j / 2 + 1], pk[j / 2 + 2], pk[j / 2 + 3]);
-          }
-        }
-        if (p.stats != nullptr) {
-          // statistics of the values as stored (bf16-rounded), masked rows contribute zero
-#pragma unroll
-          for (int j = 0; j < CH / 2; ++j) {
-            const float2 f = unpack_bf16x2(pk[j]);
-            v[2 * j] = valid ? f.x : 0.f;
-            v[2 * j + 1] = valid ? f.y : 0.f;
-          }
-        }
-      } else if (p.out_mode == CTU_OUT_F32_ROWS) {
-        if (valid) {
-          float* op = reinterpret_cast<float*>(p.out) + out_row * p.ldc + ocol;
-#pragma unroll
-          for (int j = 0; j < CH; j += 4) {
-            if (gcol + j < p.n_real) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-        }
-        if (p.stats != nullptr) {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = valid ? v[j] : 0.f;
-        }
-      } else {  // CTU_OUT_F32_CF: lanes hold consecutive voxels, so each column is a coalesced 128-byte store
-        if (valid) {
-          const long long S = (long long)p.d1 * p.d2 * p.d3;
-          const long long s_idx = ((long long)v3 * p.d2 + v2) * p.d1 + v1;
-          float* op = reinterpret_cast<float*>(p.out) + ((long long)t4 * p.n_real) * S + s_idx;
+        const int gcol = n0 + c0;  // column in the GEMM's N space (bias / stats / n_real)
+        if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < CH; ++j)
-            if (gcol + j < p.n_real) op[(long long)(gcol + j) * S] = v[j];
+            if (gcol + j < p.n_real) v[j] += __ldg(p.bias + gcol + j);
         }
-      }
-
-      if (p.stats != nullptr) {
-        float sq[32];
+        if (p.act == CTU_ACT_GELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-        const float s_sum = warp_transpose_reduce(v, lane);
-        const float s_sq = warp_transpose_reduce(sq, lane);
-        if (lane < CH) stat_scratch[q * BN + c0 + lane] = make_float2(s_sum, s_sq);
-      }
-    }
+          for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
+        }
+        const int ocol = p.out_col0 + colbase + c0;  // column inside an output row
+        if (p.res_mode == CTU_RES_F32 && valid) {
+          const float* rp = reinterpret_cast<const float*>(p.residual) + out_row * p.ldr + ocol;
+#pragma unroll
+          for (int j = 0; j < CH; j += 4) {
+            if (gcol + j < p.n_real) {
+              const float4 rv = *reinterpret_cast<const float4*>(rp + j);
+              v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
+            }
+          }
+        } else if (p.res_mode == CTU_RES_BF16 && valid) {
+          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + out_row * p.ldr + ocol;
+#pragma unroll
+          for (int j = 0; j < CH; j += 8) {
+            if (gcol + j < p.n_real) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(rp + j);
+              float2 f;
+              f = unpack_bf16x2(rv.x); v[j] += f.x; v[j + 1] += f.y;
+              f = unpack_bf16x2(rv.y); v[j + 2] += f.x; v[j + 3] += f.y;
+              f = unpack_bf16x2(rv.z); v[j + 4] += f.x; v[j + 5] += f.y;
+              f = unpack_bf16x2(rv.w); v[j + 6] += f.x; v[j + 7] += f.y;
+            }
+          }
+        }
 
-    if (p.stats != nullptr) {
-      named_bar_sync(1, 128);
-      const int e = threadIdx.x - 64;  // 0..127
-      for (int c = e; c < BN; c += 128) {
-        if (n0 + c < p.n_real) {
-          const float2 s0 = stat_scratch[c], s1 = stat_scratch[BN + c], s2 = stat_scratch[2 * BN + c],
-                       s3 = stat_scratch[3 * BN + c];
-          double* dst = p.stats + ((long long)t4 * p.stats_ld + n0 + c) * 2;
-          atomicAdd(dst, (double)s0.x + (double)s1.x + (double)s2.x + (double)s3.x);
-          atomicAdd(dst + 1, (double)s0.y + (double)s1.y + (double)s2.y + (double)s3.y);
+        if (p.out_mode == CTU_OUT_BF16_ROWS) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          if (use_tma) {
+            // SWIZZLE_128B staging: row r at r*128, 16-byte chunk c at position (c ^ (r & 7)); the TMA store clips
+            // rows / columns outside the output tensor
+            if constexpr (CH == 32 && SLABS > 0) {
+              const uint32_t base = smem_u32(cbuf) + (uint32_t)((c0 >> 6) * SLAB_BYTES + r * 128);
+              const int cb = (c0 & 63) >> 3;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t addr = base + (uint32_t)(((cb + i) ^ (r & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
+                             "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                             : "memory");
+              }
+            }
+          } else if (valid) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldc + ocol;
+#pragma unroll
+            for (int j = 0; j < CH; j += 8) {
+              if (gcol + j < p.n_real)
+                *reinterpret_cast<uint4*>(op + j) = make_uint4(pk[j / 2], pk[j / 2 + 1], pk[j / 2 + 2], pk[j / 2 + 3]);
+            }
+          }
+          if (p.stats != nullptr) {
+            // statistics of the values as stored (bf16-rounded), masked rows contribute zero
+#pragma unroll
+            for (int j = 0; j < CH / 2; ++j) {
+              const float2 f = unpack_bf16x2(pk[j]);
+              v[2 * j] = valid ? f.x : 0.f;
+              v[2 * j + 1] = valid ? f.y : 0.f;
+            }
+          }
+        } else if (p.out_mode == CTU_OUT_F32_ROWS) {
+          if (valid) {
+            float* op = reinterpret_cast<float*>(p.out) + out_row * p.ldc + ocol;
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) {
+              if (gcol + j < p.n_real) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          }
+          if (p.stats != nullptr) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = valid ? v[j] : 0.f;
+          }
+        } else {  // CTU_OUT_F32_CF: lanes hold consecutive voxels, so each column is a coalesced 128-byte store
+          if (valid) {
+            const long long S = (long long)p.d1 * p.d2 * p.d3;
+            const long long s_idx = ((long long)v3 * p.d2 + v2) * p.d1 + v1;
+            float* op = reinterpret_cast<float*>(p.out) + ((long long)tc.t4 * p.n_real) * S + s_idx;
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (gcol + j < p.n_real) op[(long long)(gcol + j) * S] = v[j];
+          }
+        }
+
+        if (p.stats != nullptr) {
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+          const float s_sum = warp_transpose_reduce(v, lane);
+          const float s_sq = warp_transpose_reduce(sq, lane);
+          if (lane < CH) stat_scratch[q * BN + c0 + lane] = make_float2(s_sum, s_sq);
+        }
+      }
+
+      // accumulator fully read: hand it back to the MMA warp before the (slower) global write-back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[slot]));
+
+      if (sync_tiles) {
+        if (use_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        named_bar_sync(2, 128);
+        if (use_tma && e == 0) {
+          if constexpr (SLABS > 0) {
+#pragma unroll
+            for (int sl = 0; sl < SLABS; ++sl) {
+              if (n0 + sl * 64 < p.n_real) {
+                asm volatile(
+                    "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(&tmC),
+                    "r"(smem_u32(cbuf + sl * SLAB_BYTES)), "r"(n0 + sl * 64), "r"(tc.x1), "r"(tc.x2), "r"(tc.x3), "r"(tc.t4)
+                    : "memory");
+              }
+            }
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (p.stats != nullptr) {
+          // per-CTA running column sums (the host sizes the grid as a multiple of n_tiles, so a CTA always works on
+          // the same N tile); flushed with fp64 atomics only when the batch item changes and at the end
+          if (tc.t4 != stat_batch) {
+            flush_stats(stat_batch);
+            stat_batch = tc.t4;
+          }
+#pragma unroll
+          for (int k = 0; k < STAT_PER_THREAD; ++k) {
+            const int c = e + 128 * k;
+            if (c < BN) {
+              const float2 s0 = stat_scratch[c], s1 = stat_scratch[BN + c], s2 = stat_scratch[2 * BN + c],
+                           s3 = stat_scratch[3 * BN + c];
+              acc_s[k] += (s0.x + s1.x) + (s2.x + s3.x);
+              acc_q[k] += (s0.y + s1.y) + (s2.y + s3.y);
+            }
+          }
         }
       }
     }
+    if (p.stats != nullptr) flush_stats(stat_batch);
+    if (use_tma && e == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -291,22 +430,39 @@ __global__ void __launch_bounds__(192) umma_gemm_kernel(const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int OUT_BUFS>
 constexpr int gemm_smem_bytes() {
-  return 1024 + STAGES * (A_STAGE_BYTES + BN * BLOCK_K * 2) + (2 * STAGES + 1) * 8 + 16 + 4 * BN * 8;
+  return 1024 + STAGES * (A_STAGE_BYTES + BN * BLOCK_K * 2) + OUT_BUFS * (BN / 64) * SLAB_BYTES + (2 * STAGES + 4) * 8 +
+         16 + 4 * BN * 8;
 }
 
-template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
+static int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  return n;
+}
+
+template <int BN, int STAGES, int OUT_BUFS, int CTAS_PER_SM>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                        cudaStream_t stream) {
-  constexpr int smem = gemm_smem_bytes<BN, STAGES>();
+  constexpr int smem = gemm_smem_bytes<BN, STAGES, OUT_BUFS>();
+  static_assert(CTAS_PER_SM * (smem + 1024) <= 228 * 1024, "shared memory budget");
+  static_assert(CTAS_PER_SM * 2 * BN <= 512, "TMEM budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<BN, STAGES, OUT_BUFS, CTAS_PER_SM>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  umma_gemm_kernel<BN, STAGES><<<grid, 192, smem, stream>>>(tmA, tmB, p);
+  // grid: persistent CTAs, a multiple of n_tiles so that every CTA keeps one N tile (per-CTA statistics, L2 reuse)
+  int cap = sm_count() * CTAS_PER_SM;
+  if (cap > p.n_tiles) cap -= cap % p.n_tiles;
+  const int grid = p.total_tiles < cap ? p.total_tiles : cap;
+  umma_gemm_kernel<BN, STAGES, OUT_BUFS, CTAS_PER_SM><<<grid, 192, smem, stream>>>(tmA, tmB, tmC, p);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -339,9 +495,10 @@ extern "C" int ctu_umma_gemm(const ctu_gemm_desc* d, void* stream_) {
   if (d->stats != nullptr && d->out_mode == CTU_OUT_F32_CF) return CTU_E_UNSUPPORTED;
   if (!tma_encoder()) return CTU_E_DRIVER;
 
-  // A: 5-D channels-last tensor map (C, d1, d2, d3, d4)
-  CUtensorMap tmA, tmB;
+  const CUtensorMapL2promotion l2p = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  CUtensorMap tmA, tmB, tmC;
   {
+    // A: 5-D channels-last tensor map (C, d1, d2, d3, d4)
     cuuint64_t dims[5] = {(cuuint64_t)d->a_c, (cuuint64_t)d->d1, (cuuint64_t)d->d2, (cuuint64_t)d->d3, (cuuint64_t)d->d4};
     cuuint64_t strides[4];
     strides[0] = (cuuint64_t)d->lda * 2;
@@ -351,8 +508,8 @@ extern "C" int ctu_umma_gemm(const ctu_gemm_desc* d, void* stream_) {
     cuuint32_t box[5] = {(cuuint32_t)BLOCK_K, (cuuint32_t)d->b1, (cuuint32_t)d->b2, (cuuint32_t)d->b3, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = tma_encoder()(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->a), dims, strides, box,
-                               es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return CTU_E_DRIVER;
   }
   {
@@ -361,9 +518,28 @@ extern "C" int ctu_umma_gemm(const ctu_gemm_desc* d, void* stream_) {
     cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)d->block_n};
     cuuint32_t es[2] = {1, 1};
     CUresult r = tma_encoder()(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), dims, strides, box,
-                               es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return CTU_E_DRIVER;
+  }
+  // C: bf16 row outputs of plain GEMMs / convs go through a swizzled smem tile and TMA stores
+  const bool tma_store = d->out_mode == CTU_OUT_BF16_ROWS && d->convt_cout == 0 && d->block_n >= 64;
+  if (tma_store) {
+    cuuint64_t dims[5] = {(cuuint64_t)d->n_real, (cuuint64_t)d->d1, (cuuint64_t)d->d2, (cuuint64_t)d->d3, (cuuint64_t)d->d4};
+    cuuint64_t strides[4];
+    strides[0] = (cuuint64_t)d->ldc * 2;
+    strides[1] = strides[0] * d->d1;
+    strides[2] = strides[1] * d->d2;
+    strides[3] = strides[2] * d->d3;
+    cuuint32_t box[5] = {64, (cuuint32_t)d->b1, (cuuint32_t)d->b2, (cuuint32_t)d->b3, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    void* base = reinterpret_cast<__nv_bfloat16*>(d->out) + d->out_col0;
+    CUresult r = tma_encoder()(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return CTU_E_DRIVER;
+  } else {
+    tmC = tmA;  // unused
   }
 
   GemmParams p;
@@ -386,16 +562,26 @@ extern "C" int ctu_umma_gemm(const ctu_gemm_desc* d, void* stream_) {
   p.u2 = d->convt_cout > 0 ? d->u2 : 1;
   p.u3 = d->convt_cout > 0 ? d->u3 : 1;
   p.stats_ld = d->stats_ld; p.out_col0 = d->out_col0;
-  const long long grid_ll = (long long)p.T1 * p.T2 * p.T3 * d->d4 * p.n_tiles;
-  if (grid_ll <= 0 || grid_ll > 0x7fffffffLL) return CTU_E_BADARG;
-  const int grid = (int)grid_ll;
+  p.tma_store = tma_store ? 1 : 0;
+  const long long tiles_ll = (long long)p.T1 * p.T2 * p.T3 * d->d4 * p.n_tiles;
+  if (tiles_ll <= 0 || tiles_ll > 0x7fffffffLL) return CTU_E_BADARG;
+  p.total_tiles = (int)tiles_ll;
 
+  // Launch shape: K-heavy tiles (convolutions) run two CTAs per SM — two MMA issuers and two TMA streams hide the
+  // shared-memory-bound operand feed of small-N tcgen05.mma; thin-K GEMMs run one CTA per SM with a deep ring.
+  // Two (or three) persistent CTAs per SM: several MMA issuers / TMA streams per SM hide the latency of the
+  // shared-memory-fed small-N tcgen05.mma and overlap one CTA's epilogue with another's main loop (measured: the
+  // 64->64 conv at 96^3 runs 1.11 ms with 2 CTAs x 3 stages against 2.05 ms with 1 CTA x 6 stages).
+  static const int variant = [] { const char* e = getenv("CTU_GEMM_VARIANT"); return e ? atoi(e) : 0; }();
   switch (d->block_n) {
-    case 16: return launch_gemm<16, 4>(tmA, tmB, p, grid, stream);
-    case 32: return launch_gemm<32, 4>(tmA, tmB, p, grid, stream);
-    case 64: return launch_gemm<64, 4>(tmA, tmB, p, grid, stream);
-    case 128: return launch_gemm<128, 3>(tmA, tmB, p, grid, stream);
-    case 256: return launch_gemm<256, 4>(tmA, tmB, p, grid, stream);
+    case 16: return launch_gemm<16, 4, 0, 2>(tmA, tmB, tmC, p, stream);
+    case 32: return launch_gemm<32, 4, 0, 2>(tmA, tmB, tmC, p, stream);
+    case 64:
+      // 3x3x3 convolutions with 64 output channels: three CTAs per SM (measured 1.04 vs 1.10 ms at 96^3 x 4)
+      if (variant == 3 || (variant == 0 && p.num_kb >= 27)) return launch_gemm<64, 2, 1, 3>(tmA, tmB, tmC, p, stream);
+      return launch_gemm<64, 3, 1, 2>(tmA, tmB, tmC, p, stream);
+    case 128: return launch_gemm<128, 2, 1, 2>(tmA, tmB, tmC, p, stream);
+    case 256: return launch_gemm<256, 3, 1, 1>(tmA, tmB, tmC, p, stream);
     default: return CTU_E_UNSUPPORTED;
   }
 }
