@@ -10,11 +10,28 @@ SIGS = {
     "ctu_patchify_ln": (P, I, I, I, I, I, P, P, P, F, P),
     "ctu_pwa_fuse": (P, P, P, L, I, I, P),
     "ctu_subsample": (P, I, I, I, I, P, I, I, I, I, I, I, P),
-    "ctu_attention": (P, I, I, I, P, I, P, I, I, I, I, I, I, I, I, P),
+    "ctu_attention": (P, I, I, I, P, I, P, I, I, I, I, I, I, I, I, P, P),
     "ctu_conv_cin1": (P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, I, I, P),
     "ctu_blend_accumulate": (P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P),
     "ctu_blend_count": (P, P, I, I, I, I, I, I, I, I, I, P),
     "ctu_blend_normalize": (P, P, P, I, L, P),
+    # backward pass
+    "ctu_in_bwd_stats": (P, I, P, I, P, I, P, I, P, I, P, I, I, L, I, F, I, F, P, P),
+    "ctu_in_bwd_apply": (P, I, P, I, P, I, P, I, P, I, P, I, I, I, L, I, F, I, F, P, P, I, P, I, P),
+    "ctu_layernorm_bwd": (P, I, L, P, P, L, P, I, L, P, L, P, L, P, P, L, I, F, P),
+    "ctu_gelu": (P, P, L, P),
+    "ctu_gelu_bwd": (P, P, P, L, P),
+    "ctu_pwa_fuse_bwd": (P, P, P, P, P, L, I, I, P),
+    "ctu_colsum": (P, I, L, L, L, P, P),
+    "ctu_cf_to_cl": (P, P, I, I, L, I, I, P),
+    "ctu_space_to_depth": (P, I, P, I, I, I, I, I, I, I, I, P),
+    "ctu_subsample_bwd": (P, I, P, I, I, I, I, I, I, I, I, I, I, P),
+    "ctu_im2col_cin1": (P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, I, P),
+    "ctu_accumulate": (P, L, P, L, L, I, I, P),
+    "ctu_cast_f32_bf16": (P, L, P, L, L, I, P),
+    "ctu_patchify_ln_bwd": (P, I, I, I, I, I, P, P, P, F, P),
+    "ctu_attention_delta": (P, L, P, L, P, L, I, I, P),
+    "ctu_attention_bwd": (P, I, I, I, P, I, P, P, P, P, I, P, P, I, I, I, I, I, I, I, I, P),
 }
 
 

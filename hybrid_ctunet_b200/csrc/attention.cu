@@ -6,45 +6,11 @@
 // mma.sync m16n8k16 (bf16 in, fp32 accumulate) with the whole K/V of one (window, head) resident in shared
 // memory.  The window / grid partition of the reference's einops rearranges is folded into the row gather,
 // so activations never leave their natural channels-last order.
-#include "common.cuh"
+#include "attention_common.cuh"
 #include "../../include/ctunet_b200.h"
 #include "host_util.h"
 
 namespace ctu {
-
-struct TokenMap {
-  int mode;           // 0: rows = win*n + p; 1: block partition '(h h1)'; 2: grid partition '(h1 h)'
-  int X, Y, Z;        // token grid of one batch item
-  int nwx, nwy, nwz;  // windows per axis
-  int w;              // window edge (6)
-};
-
-__device__ __forceinline__ long long token_row(const TokenMap& m, int win, int p, int n) {
-  if (m.mode == 0) return (long long)win * n + p;
-  const int wz = win % m.nwz;
-  int t = win / m.nwz;
-  const int wy = t % m.nwy;
-  t /= m.nwy;
-  const int wx = t % m.nwx;
-  const int b = t / m.nwx;
-  const int pz = p % m.w;
-  const int py = (p / m.w) % m.w;
-  const int px = p / (m.w * m.w);
-  int x, y, z;
-  if (m.mode == 1) {
-    x = wx * m.w + px; y = wy * m.w + py; z = wz * m.w + pz;
-  } else {
-    x = px * m.nwx + wx; y = py * m.nwy + wy; z = pz * m.nwz + wz;
-  }
-  return (((long long)b * m.X + x) * m.Y + y) * m.Z + z;
-}
-
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 constexpr int KCHUNK = 48;  // keys per online-softmax step (3 k-tiles of 16)
 
@@ -52,7 +18,7 @@ template <int D>
 __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, int C,
                                                         __nv_bfloat16* __restrict__ out, int ldo,
                                                         const float* __restrict__ bias, float scale, int n, int n_pad,
-                                                        TokenMap map) {
+                                                        TokenMap map, float* __restrict__ lse) {
   constexpr int LDK = D + 8;
   extern __shared__ __align__(16) uint8_t smem_att[];
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_att);  // [n_pad][LDK]
@@ -172,6 +138,12 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
   l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);
   l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
   const float ia = 1.f / l_a, ib = 1.f / l_b;
+  if (lse != nullptr && t == 0) {
+    // log2-domain log-sum-exp of the scaled (+biased) scores, kept for the backward pass
+    const int heads = C / D;
+    if (va) lse[ra * heads + h] = m_a + log2f(l_a);
+    if (vb) lse[rb * heads + h] = m_b + log2f(l_b);
+  }
 #pragma unroll
   for (int dn = 0; dn < D / 8; ++dn) {
     const int c = h * D + dn * 8 + 2 * t;
@@ -189,7 +161,8 @@ using namespace ctu;
 // mode 1/2: block / grid partition of a [batch, X, Y, Z] token grid into w^3 windows (n = w^3).
 // bias: fp32 [heads][n][n] added to the scaled scores, or NULL.
 extern "C" int ctu_attention(const void* qkv, int ld_qkv, int C, int dim_head, void* out, int ldo, const float* bias,
-                             int n, int windows, int mode, int batch, int X, int Y, int Z, int w, void* stream) {
+                             int n, int windows, int mode, int batch, int X, int Y, int Z, int w, float* lse,
+                             void* stream) {
   if (!qkv || !out || (dim_head != 32 && dim_head != 64) || C % dim_head || ld_qkv % 8 || ldo % 2) return CTU_E_BADARG;
   TokenMap m;
   m.mode = mode; m.X = X; m.Y = Y; m.Z = Z; m.w = w;
@@ -218,10 +191,10 @@ extern "C" int ctu_attention(const void* qkv, int ld_qkv, int C, int dim_head, v
   }
   if (dim_head == 64) {
     attention_kernel<64><<<grid, 128, smem, st>>>((const __nv_bfloat16*)qkv, ld_qkv, C, (__nv_bfloat16*)out, ldo, bias,
-                                                  scale, n, n_pad, m);
+                                                  scale, n, n_pad, m, lse);
   } else {
     attention_kernel<32><<<grid, 128, smem, st>>>((const __nv_bfloat16*)qkv, ld_qkv, C, (__nv_bfloat16*)out, ldo, bias,
-                                                  scale, n, n_pad, m);
+                                                  scale, n, n_pad, m, lse);
   }
   count_launch();
   return (int)cudaGetLastError();

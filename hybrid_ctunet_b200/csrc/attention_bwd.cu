@@ -1,0 +1,320 @@
+// Backward of the fused softmax(Q K^T * scale + bias) V of attention.cu (sm_100a), for ViT MHSA (vit.py:66-78)
+// and MultiAxisAttention (hybrid_CTUNet.py:481-511).  Same mma.sync m16n8k16 machinery as the forward:
+// a CTA owns 64 keys (16 per warp) of one (window, head) and streams the queries in chunks of 32 through
+// shared memory, recomputing P^T = exp2(S^T - lse) from the log-sum-exp the forward saved:
+//   dV  += P^T dO            dP^T = V dO^T          dS^T = P^T o (dP^T - delta),  delta = rowsum(dO o O)
+//   dK  += dS^T Q * scale    dQ   += dS K * scale   dBias = dS (summed over windows by ctu_colsum afterwards)
+// dK / dV rows are owned by exactly one warp and written as bf16; dQ gets contributions from every key block,
+// so it is reduced across the CTA's warps in shared memory (shared atomics) and added to an fp32 buffer with
+// vector reductions.
+#include "attention_common.cuh"
+#include "../../include/ctunet_b200.h"
+#include "host_util.h"
+
+namespace ctu {
+
+constexpr int QC = 32;          // queries per chunk
+constexpr int LDT = QC + 8;     // row pitch of the transposed chunk copies
+
+// delta[row][h] = sum_d dO[row][h*D + d] * O[row][h*D + d]
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long ldo,
+                                                         const __nv_bfloat16* __restrict__ dout, long long ldd,
+                                                         float* __restrict__ delta, long long rows, int C, int D) {
+  const int tpr = C / 8;
+  const int lph = D / 8;  // lanes per head: 4 or 8
+  const long long total = rows * tpr;
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
+    long long i = base + threadIdx.x;
+    const bool ok = i < total;
+    if (!ok) i = total - 1;
+    const long long r = i / tpr;
+    const int cv = (int)(i - r * tpr);
+    const uint4 a = *reinterpret_cast<const uint4*>(o + r * ldo + cv * 8);
+    const uint4 b = *reinterpret_cast<const uint4*>(dout + r * ldd + cv * 8);
+    float2 x, y;
+    float s = 0.f;
+    x = unpack_bf16x2(a.x); y = unpack_bf16x2(b.x); s += x.x * y.x + x.y * y.y;
+    x = unpack_bf16x2(a.y); y = unpack_bf16x2(b.y); s += x.x * y.x + x.y * y.y;
+    x = unpack_bf16x2(a.z); y = unpack_bf16x2(b.z); s += x.x * y.x + x.y * y.y;
+    x = unpack_bf16x2(a.w); y = unpack_bf16x2(b.w); s += x.x * y.x + x.y * y.y;
+    for (int off = 1; off < lph; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (ok && (cv % lph) == 0) delta[r * (C / D) + cv / lph] = s;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, int C,
+                                                            const __nv_bfloat16* __restrict__ dout, int ldd,
+                                                            const float* __restrict__ lse, const float* __restrict__ delta,
+                                                            const float* __restrict__ biasT, float scale,
+                                                            __nv_bfloat16* __restrict__ dqkv, int ld_dqkv,
+                                                            float* __restrict__ dq_f32, __nv_bfloat16* __restrict__ ds_out,
+                                                            int n, TokenMap map) {
+  constexpr int LDQ = D + 8;
+  constexpr int LDK = 16 + 8;
+  __shared__ __align__(16) __nv_bfloat16 Qs[QC * LDQ];
+  __shared__ __align__(16) __nv_bfloat16 dOs[QC * LDQ];
+  __shared__ __align__(16) __nv_bfloat16 Qt[D * LDT];
+  __shared__ __align__(16) __nv_bfloat16 dOt[D * LDT];
+  __shared__ __align__(16) __nv_bfloat16 Ktw[4][D * LDK];
+  __shared__ __align__(16) __nv_bfloat16 patch[4][16 * LDK];
+  __shared__ __align__(16) float dQs[QC * D];
+  __shared__ float lse_s[QC], delta_s[QC];
+  __shared__ long long qrow_s[QC];
+
+  const int kb = blockIdx.x, h = blockIdx.y, win = blockIdx.z;
+  const int heads = C / D;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const float LOG2E = 1.4426950408889634f;
+  const float sl = scale * LOG2E;
+
+  // ---- this warp's 16 keys: K and V as A fragments (rows = keys), K^T in shared memory for the dQ product
+  const int key0 = kb * 64 + warp * 16;
+  const int ka = key0 + g, kbk = key0 + g + 8;
+  const bool va = ka < n, vb = kbk < n;
+  const long long ra = va ? token_row(map, win, ka, n) : 0;
+  const long long rb = vb ? token_row(map, win, kbk, n) : 0;
+  uint32_t kf[D / 16][4], vf[D / 16][4];
+#pragma unroll
+  for (int kk = 0; kk < D / 16; ++kk) {
+    const int c = h * D + kk * 16 + 2 * t;
+    kf[kk][0] = va ? *reinterpret_cast<const uint32_t*>(qkv + ra * ld_qkv + C + c) : 0u;
+    kf[kk][1] = vb ? *reinterpret_cast<const uint32_t*>(qkv + rb * ld_qkv + C + c) : 0u;
+    kf[kk][2] = va ? *reinterpret_cast<const uint32_t*>(qkv + ra * ld_qkv + C + c + 8) : 0u;
+    kf[kk][3] = vb ? *reinterpret_cast<const uint32_t*>(qkv + rb * ld_qkv + C + c + 8) : 0u;
+    vf[kk][0] = va ? *reinterpret_cast<const uint32_t*>(qkv + ra * ld_qkv + 2 * C + c) : 0u;
+    vf[kk][1] = vb ? *reinterpret_cast<const uint32_t*>(qkv + rb * ld_qkv + 2 * C + c) : 0u;
+    vf[kk][2] = va ? *reinterpret_cast<const uint32_t*>(qkv + ra * ld_qkv + 2 * C + c + 8) : 0u;
+    vf[kk][3] = vb ? *reinterpret_cast<const uint32_t*>(qkv + rb * ld_qkv + 2 * C + c + 8) : 0u;
+  }
+  {
+    __nv_bfloat16* kt = Ktw[warp];
+    for (int i = lane; i < 16 * (D / 8); i += 32) {
+      const int j = i / (D / 8), vi = i % (D / 8);
+      uint4 kv = make_uint4(0, 0, 0, 0);
+      if (key0 + j < n) kv = *reinterpret_cast<const uint4*>(qkv + token_row(map, win, key0 + j, n) * ld_qkv + C + h * D + vi * 8);
+      const __nv_bfloat16* ke = reinterpret_cast<const __nv_bfloat16*>(&kv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) kt[(vi * 8 + e) * LDK + j] = ke[e];
+    }
+  }
+
+  float dk[D / 8][4], dv[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
+
+  const float* bT_a = biasT ? biasT + ((long long)h * n + (va ? ka : 0)) * n : nullptr;
+  const float* bT_b = biasT ? biasT + ((long long)h * n + (vb ? kbk : 0)) * n : nullptr;
+  __nv_bfloat16* ds_a = ds_out ? ds_out + (((long long)win * heads + h) * n + (va ? ka : 0)) * n : nullptr;
+  __nv_bfloat16* ds_b = ds_out ? ds_out + (((long long)win * heads + h) * n + (vb ? kbk : 0)) * n : nullptr;
+
+  const int n_chunks = (n + QC - 1) / QC;
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int q0 = ch * QC;
+    __syncthreads();  // the previous chunk's readers of the staging buffers are done
+    // ---- stage Q, dO (row-major and transposed), lse, delta of this query chunk
+    if (tid < QC) {
+      const int q = q0 + tid;
+      const bool ok = q < n;
+      const long long row = ok ? token_row(map, win, q, n) : 0;
+      qrow_s[tid] = ok ? row : -1;
+      lse_s[tid] = ok ? lse[row * heads + h] : INFINITY;
+      delta_s[tid] = ok ? delta[row * heads + h] : 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < QC * D / 4; i += 128) *reinterpret_cast<float4*>(dQs + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < QC * (D / 8); i += 128) {
+      const int j = i / (D / 8), vi = i % (D / 8);
+      const long long row = qrow_s[j];
+      uint4 qv = make_uint4(0, 0, 0, 0), gv = make_uint4(0, 0, 0, 0);
+      if (row >= 0) {
+        qv = *reinterpret_cast<const uint4*>(qkv + row * ld_qkv + h * D + vi * 8);
+        gv = *reinterpret_cast<const uint4*>(dout + row * ldd + h * D + vi * 8);
+      }
+      *reinterpret_cast<uint4*>(Qs + j * LDQ + vi * 8) = qv;
+      *reinterpret_cast<uint4*>(dOs + j * LDQ + vi * 8) = gv;
+      const __nv_bfloat16* qe = reinterpret_cast<const __nv_bfloat16*>(&qv);
+      const __nv_bfloat16* ge = reinterpret_cast<const __nv_bfloat16*>(&gv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        Qt[(vi * 8 + e) * LDT + j] = qe[e];
+        dOt[(vi * 8 + e) * LDT + j] = ge[e];
+      }
+    }
+    __syncthreads();
+
+    // ---- S^T and dP^T for 16 keys x 32 queries (four 8-query sub-tiles)
+    float s[QC / 8][4], dp[QC / 8][4];
+#pragma unroll
+    for (int qs = 0; qs < QC / 8; ++qs) {
+      s[qs][0] = s[qs][1] = s[qs][2] = s[qs][3] = 0.f;
+      dp[qs][0] = dp[qs][1] = dp[qs][2] = dp[qs][3] = 0.f;
+      const __nv_bfloat16* qp = Qs + (qs * 8 + g) * LDQ + 2 * t;
+      const __nv_bfloat16* gp = dOs + (qs * 8 + g) * LDQ + 2 * t;
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk) {
+        mma_bf16_16816(s[qs], kf[kk], *reinterpret_cast<const uint32_t*>(qp + kk * 16),
+                       *reinterpret_cast<const uint32_t*>(qp + kk * 16 + 8));
+        mma_bf16_16816(dp[qs], vf[kk], *reinterpret_cast<const uint32_t*>(gp + kk * 16),
+                       *reinterpret_cast<const uint32_t*>(gp + kk * 16 + 8));
+      }
+    }
+    // ---- P^T and dS^T (rows: keys g / g+8, columns: queries 2t, 2t+1 of each sub-tile)
+    uint32_t pA[QC / 16][4], dsA[QC / 16][4];
+#pragma unroll
+    for (int qs = 0; qs < QC / 8; ++qs) {
+      const int ql = qs * 8 + 2 * t;
+      const int q = q0 + ql;
+      float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+      if (biasT != nullptr && q < n) {
+        const float2 x = *reinterpret_cast<const float2*>(bT_a + q);
+        const float2 y = *reinterpret_cast<const float2*>(bT_b + q);
+        b0 = x.x * LOG2E; b1 = x.y * LOG2E; b2 = y.x * LOG2E; b3 = y.y * LOG2E;
+      }
+      const float l0 = lse_s[ql], l1 = lse_s[ql + 1];
+      const float d0 = delta_s[ql], d1 = delta_s[ql + 1];
+      const float p0 = va ? exp2f(fmaf(s[qs][0], sl, b0) - l0) : 0.f;
+      const float p1 = va ? exp2f(fmaf(s[qs][1], sl, b1) - l1) : 0.f;
+      const float p2 = vb ? exp2f(fmaf(s[qs][2], sl, b2) - l0) : 0.f;
+      const float p3 = vb ? exp2f(fmaf(s[qs][3], sl, b3) - l1) : 0.f;
+      const float e0 = p0 * (dp[qs][0] - d0), e1 = p1 * (dp[qs][1] - d1);
+      const float e2 = p2 * (dp[qs][2] - d0), e3 = p3 * (dp[qs][3] - d1);
+      pA[qs >> 1][(qs & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pA[qs >> 1][(qs & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      const uint32_t e01 = pack_bf16x2(e0, e1), e23 = pack_bf16x2(e2, e3);
+      dsA[qs >> 1][(qs & 1) * 2 + 0] = e01;
+      dsA[qs >> 1][(qs & 1) * 2 + 1] = e23;
+      if (ds_out != nullptr && q < n) {
+        if (va) *reinterpret_cast<uint32_t*>(ds_a + q) = e01;
+        if (vb) *reinterpret_cast<uint32_t*>(ds_b + q) = e23;
+      }
+    }
+    // ---- dV += P^T dO, dK += dS^T Q  (contraction over the 32 queries)
+#pragma unroll
+    for (int kt = 0; kt < QC / 16; ++kt) {
+#pragma unroll
+      for (int dn = 0; dn < D / 8; ++dn) {
+        const __nv_bfloat16* gp = dOt + (dn * 8 + g) * LDT + kt * 16 + 2 * t;
+        mma_bf16_16816(dv[dn], pA[kt], *reinterpret_cast<const uint32_t*>(gp), *reinterpret_cast<const uint32_t*>(gp + 8));
+        const __nv_bfloat16* qp = Qt + (dn * 8 + g) * LDT + kt * 16 + 2 * t;
+        mma_bf16_16816(dk[dn], dsA[kt], *reinterpret_cast<const uint32_t*>(qp), *reinterpret_cast<const uint32_t*>(qp + 8));
+      }
+    }
+    // ---- dQ partial of this warp: (16 queries x 16 keys) . (16 keys x D), two 16-query tiles
+    __nv_bfloat16* pp = patch[warp];
+    const __nv_bfloat16* kt_s = Ktw[warp];
+#pragma unroll
+    for (int mt = 0; mt < QC / 16; ++mt) {
+      __syncwarp();
+      // transpose through the per-warp patch: patch[query][key]
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t u01 = dsA[mt][half * 2 + 0], u23 = dsA[mt][half * 2 + 1];
+        const __nv_bfloat162 v01 = *reinterpret_cast<const __nv_bfloat162*>(&u01);
+        const __nv_bfloat162 v23 = *reinterpret_cast<const __nv_bfloat162*>(&u23);
+        const int qa = half * 8 + 2 * t;
+        pp[qa * LDK + g] = v01.x;
+        pp[(qa + 1) * LDK + g] = v01.y;
+        pp[qa * LDK + g + 8] = v23.x;
+        pp[(qa + 1) * LDK + g + 8] = v23.y;
+      }
+      __syncwarp();
+      uint32_t af[4];
+      af[0] = *reinterpret_cast<const uint32_t*>(pp + g * LDK + 2 * t);
+      af[1] = *reinterpret_cast<const uint32_t*>(pp + (g + 8) * LDK + 2 * t);
+      af[2] = *reinterpret_cast<const uint32_t*>(pp + g * LDK + 2 * t + 8);
+      af[3] = *reinterpret_cast<const uint32_t*>(pp + (g + 8) * LDK + 2 * t + 8);
+      float* dqw = dQs + (mt * 16) * D;
+#pragma unroll
+      for (int dn = 0; dn < D / 8; ++dn) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const __nv_bfloat16* bp = kt_s + (dn * 8 + g) * LDK + 2 * t;
+        mma_bf16_16816(acc, af, *reinterpret_cast<const uint32_t*>(bp), *reinterpret_cast<const uint32_t*>(bp + 8));
+        atomicAdd(dqw + g * D + dn * 8 + 2 * t, acc[0]);
+        atomicAdd(dqw + g * D + dn * 8 + 2 * t + 1, acc[1]);
+        atomicAdd(dqw + (g + 8) * D + dn * 8 + 2 * t, acc[2]);
+        atomicAdd(dqw + (g + 8) * D + dn * 8 + 2 * t + 1, acc[3]);
+      }
+    }
+    __syncthreads();
+    // ---- reduce the four warps' dQ partials and add them to the fp32 dQ buffer
+    for (int i = tid; i < QC * (D / 4); i += 128) {
+      const int j = i / (D / 4), c4 = (i % (D / 4)) * 4;
+      const long long row = qrow_s[j];
+      if (row < 0) continue;
+      const float4 a = *reinterpret_cast<const float4*>(dQs + j * D + c4);
+      float* dst = dq_f32 + row * C + h * D + c4;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x * scale), "f"(a.y * scale),
+                   "f"(a.z * scale), "f"(a.w * scale)
+                   : "memory");
+    }
+  }
+
+  // ---- dK (scaled) and dV rows of this warp's keys
+#pragma unroll
+  for (int dn = 0; dn < D / 8; ++dn) {
+    const int c = h * D + dn * 8 + 2 * t;
+    if (va) {
+      *reinterpret_cast<uint32_t*>(dqkv + ra * ld_dqkv + C + c) = pack_bf16x2(dk[dn][0] * scale, dk[dn][1] * scale);
+      *reinterpret_cast<uint32_t*>(dqkv + ra * ld_dqkv + 2 * C + c) = pack_bf16x2(dv[dn][0], dv[dn][1]);
+    }
+    if (vb) {
+      *reinterpret_cast<uint32_t*>(dqkv + rb * ld_dqkv + C + c) = pack_bf16x2(dk[dn][2] * scale, dk[dn][3] * scale);
+      *reinterpret_cast<uint32_t*>(dqkv + rb * ld_dqkv + 2 * C + c) = pack_bf16x2(dv[dn][2], dv[dn][3]);
+    }
+  }
+}
+
+}  // namespace ctu
+
+using namespace ctu;
+
+extern "C" int ctu_attention_delta(const void* o, long long ldo, const void* dout, long long ldd, float* delta,
+                                   long long rows, int C, int dim_head, void* stream) {
+  if (!o || !dout || !delta || rows <= 0 || (dim_head != 32 && dim_head != 64) || C % dim_head || ldo % 8 || ldd % 8)
+    return CTU_E_BADARG;
+  const long long total = rows * (C / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  attn_delta_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)o, ldo,
+                                                                        (const __nv_bfloat16*)dout, ldd, delta, rows, C,
+                                                                        dim_head);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// qkv / dqkv: bf16 [rows][3C] (q|k|v); dqkv receives dK and dV, dQ is ACCUMULATED into dq_f32 (fp32 [rows][C],
+// zeroed by the caller).  biasT: fp32 [heads][n][n] indexed [key][query] or NULL; ds_out: bf16
+// [windows][heads][n][n] indexed [key][query] or NULL.
+extern "C" int ctu_attention_bwd(const void* qkv, int ld_qkv, int C, int dim_head, const void* dout, int ldd,
+                                 const float* lse, const float* delta, const float* biasT, void* dqkv, int ld_dqkv,
+                                 float* dq_f32, void* ds_out, int n, int windows, int mode, int batch, int X, int Y, int Z,
+                                 int w, void* stream) {
+  if (!qkv || !dout || !lse || !delta || !dqkv || !dq_f32) return CTU_E_BADARG;
+  if ((dim_head != 32 && dim_head != 64) || C % dim_head || ld_qkv % 8 || ldd % 8 || ld_dqkv % 8 || C % 4) return CTU_E_BADARG;
+  if ((biasT || ds_out) && (n % 2)) return CTU_E_BADARG;
+  TokenMap m;
+  m.mode = mode; m.X = X; m.Y = Y; m.Z = Z; m.w = w;
+  m.nwx = m.nwy = m.nwz = 1;
+  if (mode != 0) {
+    if (w <= 0 || X % w || Y % w || Z % w || n != w * w * w) return CTU_E_BADARG;
+    m.nwx = X / w; m.nwy = Y / w; m.nwz = Z / w;
+    windows = batch * m.nwx * m.nwy * m.nwz;
+  }
+  if (windows <= 0 || windows > 65535) return CTU_E_BADARG;
+  const int heads = C / dim_head;
+  dim3 grid((n + 63) / 64, heads, windows);
+  const float scale = 1.0f / sqrtf((float)dim_head);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dim_head == 64)
+    attention_bwd_kernel<64><<<grid, 128, 0, st>>>((const __nv_bfloat16*)qkv, ld_qkv, C, (const __nv_bfloat16*)dout, ldd, lse,
+                                                   delta, biasT, scale, (__nv_bfloat16*)dqkv, ld_dqkv, dq_f32,
+                                                   (__nv_bfloat16*)ds_out, n, m);
+  else
+    attention_bwd_kernel<32><<<grid, 128, 0, st>>>((const __nv_bfloat16*)qkv, ld_qkv, C, (const __nv_bfloat16*)dout, ldd, lse,
+                                                   delta, biasT, scale, (__nv_bfloat16*)dqkv, ld_dqkv, dq_f32,
+                                                   (__nv_bfloat16*)ds_out, n, m);
+  count_launch();
+  return (int)cudaGetLastError();
+}

@@ -36,6 +36,17 @@ class GemmDesc(C.Structure):
     ]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("dy", C.c_void_p), ("dw", C.c_void_p),
+        ("x_c", C.c_int32), ("ldx", C.c_int32), ("n", C.c_int32), ("ldy", C.c_int32), ("ldw", C.c_int32),
+        ("d1", C.c_int32), ("d2", C.c_int32), ("d3", C.c_int32), ("d4", C.c_int32),
+        ("b1", C.c_int32), ("b2", C.c_int32), ("b3", C.c_int32),
+        ("k1", C.c_int32), ("k2", C.c_int32), ("k3", C.c_int32),
+        ("block_n", C.c_int32),
+    ]
+
+
 def lib_path() -> str:
     return _build.LIB_PATH
 
@@ -70,6 +81,8 @@ def _have_nvcc() -> bool:
 def _declare(lib):
     lib.ctu_umma_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     lib.ctu_umma_gemm.restype = C.c_int
+    lib.ctu_umma_wgrad.argtypes = [C.POINTER(WgradDesc), C.c_void_p]
+    lib.ctu_umma_wgrad.restype = C.c_int
     lib.ctu_launch_count.argtypes = []
     lib.ctu_launch_count.restype = C.c_int64
     lib.ctu_device_ok.argtypes = []

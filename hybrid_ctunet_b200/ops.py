@@ -13,7 +13,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import lib as _lib
-from .lib import GemmDesc, check
+from .lib import GemmDesc, WgradDesc, check
 
 OUT_BF16, OUT_F32, OUT_F32_CF = 0, 1, 2
 ACT_NONE, ACT_GELU = 0, 1
@@ -202,13 +202,15 @@ def subsample(x: torch.Tensor, out: torch.Tensor, stride: Tuple[int, int, int]) 
 
 
 def attention(qkv: torch.Tensor, out: torch.Tensor, *, dim_head: int, n: int, windows: int = 0, mode: int = 0,
-              bias: Optional[torch.Tensor] = None, grid: Tuple[int, int, int, int] = (1, 1, 1, 1), w: int = 6):
-    """qkv: bf16 [rows, 3C]; out: bf16 [rows, C].  grid = (batch, X, Y, Z) token grid for mode 1 (block) / 2 (grid)."""
+              bias: Optional[torch.Tensor] = None, grid: Tuple[int, int, int, int] = (1, 1, 1, 1), w: int = 6,
+              lse: Optional[torch.Tensor] = None):
+    """qkv: bf16 [rows, 3C]; out: bf16 [rows, C].  grid = (batch, X, Y, Z) token grid for mode 1 (block) / 2 (grid).
+    lse: optional fp32 [rows, heads] receiving the base-2 log-sum-exp per (row, head) for the backward pass."""
     lib = _lib.require_device()
     C_ = qkv.shape[-1] // 3
     b, X, Y, Z = grid
     check(lib.ctu_attention(qkv.data_ptr(), int(qkv.stride(-2)), C_, dim_head, out.data_ptr(), int(out.stride(-2)),
-                            _ptr(bias), n, windows, mode, b, X, Y, Z, w, _stream()), "ctu_attention")
+                            _ptr(bias), n, windows, mode, b, X, Y, Z, w, _ptr(lse), _stream()), "ctu_attention")
     return out
 
 
@@ -246,3 +248,204 @@ def blend_normalize(acc, cnt, out):
     check(lib.ctu_blend_normalize(acc.data_ptr(), cnt.data_ptr(), out.data_ptr(), C_, vox, _stream()),
           "ctu_blend_normalize")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ backward pass
+def pick_wgrad_block_n(n: int) -> int:
+    if n % 256 == 0:
+        return 256
+    if n % 128 == 0:
+        return 128
+    return 64
+
+
+def wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, *, dims: Sequence[int], ksize: int = 1,
+          x_c: Optional[int] = None, n: Optional[int] = None) -> torch.Tensor:
+    """dw[(tap, ci), co] += sum_v x[v + tap - pad, ci] * dy[v, co] on the tcgen05 wgrad kernel.
+
+    x  : bf16 channels-last rows (row stride x.stride(-2)), first x_c channels used (x_c % 64 == 0).
+    dy : bf16 channels-last rows, first n channels used.
+    dw : fp32 [ksize^3 * x_c, >= n] accumulated in place (zero it first).
+    dims as for `gemm`: (d1, d2, d3, d4) with d1 fastest; (M, 1, 1, 1) for a flat token GEMM.
+    """
+    lib = _lib.require_device()
+    d1, d2, d3, d4 = (int(v) for v in dims)
+    assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16 and dw.dtype == torch.float32
+    assert x.stride(-1) == 1 and dy.stride(-1) == 1 and dw.stride(-1) == 1
+    d = WgradDesc()
+    d.x, d.dy, d.dw = x.data_ptr(), dy.data_ptr(), dw.data_ptr()
+    d.x_c = int(x_c if x_c is not None else x.shape[-1])
+    d.ldx = int(x.stride(-2))
+    d.n = int(n if n is not None else dy.shape[-1])
+    d.ldy = int(dy.stride(-2))
+    d.ldw = int(dw.stride(-2))
+    assert dw.shape[-2] == ksize ** 3 * d.x_c and dw.shape[-1] >= d.n
+    d.d1, d.d2, d.d3, d.d4 = d1, d2, d3, d4
+    d.b1, d.b2, d.b3 = pick_box(d1, d2, d3)
+    d.k1 = d.k2 = d.k3 = ksize
+    d.block_n = pick_wgrad_block_n(d.n)
+    check(lib.ctu_umma_wgrad(C.byref(d), _stream()), "ctu_umma_wgrad")
+    return dw
+
+
+def _bsc(x: torch.Tensor):
+    B, C_ = x.shape[0], x.shape[-1]
+    S = 1
+    for d in x.shape[1:-1]:
+        S *= int(d)
+    return B, S, C_
+
+
+def in_backward(dout, out, x, xstats, dx, *, res=None, rstats=None, dres=None, sums=None, act: bool = True):
+    """Backward of in_apply.  dout/out/x(/res): bf16 [B, ..., C]; writes dx (and dres when the forward had a residual:
+    the raw gradient g for an identity residual, the InstanceNorm backward for a normalised one)."""
+    lib = _lib.require_device()
+    B, S, C_ = _bsc(x)
+    if sums is None:
+        sums = torch.zeros(B, C_, 4, dtype=torch.float64, device=x.device)
+    res_mode = 0 if dres is None else (2 if rstats is not None else 1)
+    r2 = res if res_mode == 2 else None
+    check(lib.ctu_in_bwd_stats(dout.data_ptr(), int(dout.stride(-2)), out.data_ptr(), int(out.stride(-2)), x.data_ptr(),
+                               int(x.stride(-2)), xstats.data_ptr(), int(xstats.shape[-2]), _ptr(r2),
+                               0 if r2 is None else int(r2.stride(-2)), _ptr(rstats) if res_mode == 2 else None,
+                               0 if res_mode != 2 else int(rstats.shape[-2]), B, S, C_, IN_EPS, 1 if act else 0,
+                               LRELU_SLOPE, sums.data_ptr(), _stream()), "ctu_in_bwd_stats")
+    check(lib.ctu_in_bwd_apply(dout.data_ptr(), int(dout.stride(-2)), out.data_ptr(), int(out.stride(-2)), x.data_ptr(),
+                               int(x.stride(-2)), xstats.data_ptr(), int(xstats.shape[-2]), _ptr(r2),
+                               0 if r2 is None else int(r2.stride(-2)), _ptr(rstats) if res_mode == 2 else None,
+                               0 if res_mode != 2 else int(rstats.shape[-2]), res_mode, B, S, C_, IN_EPS,
+                               1 if act else 0, LRELU_SLOPE, sums.data_ptr(), dx.data_ptr(), int(dx.stride(-2)),
+                               _ptr(dres), 0 if dres is None else int(dres.stride(-2)), _stream()), "ctu_in_bwd_apply")
+    return dx
+
+
+def layernorm_backward(x, gamma, dy, dgamma, dbeta, *, dx_in=None, dx_f32=None, dx_bf16=None, eps: float = 1e-5):
+    """x: [M, C] fp32/bf16; dy: bf16 [M, C]; dgamma/dbeta: fp32 [C] accumulated; dx (+ dx_in) -> dx_f32 and/or dx_bf16."""
+    lib = _lib.require_device()
+    C_ = x.shape[-1]
+    M = x.numel() // C_ if x.is_contiguous() else x.shape[0]
+    check(lib.ctu_layernorm_bwd(x.data_ptr(), int(x.dtype == torch.float32), int(x.stride(-2)), gamma.data_ptr(),
+                                dy.data_ptr(), int(dy.stride(-2)), _ptr(dx_in),
+                                0 if dx_in is None else int(dx_in.dtype == torch.float32),
+                                0 if dx_in is None else int(dx_in.stride(-2)), _ptr(dx_f32),
+                                0 if dx_f32 is None else int(dx_f32.stride(-2)), _ptr(dx_bf16),
+                                0 if dx_bf16 is None else int(dx_bf16.stride(-2)), dgamma.data_ptr(), dbeta.data_ptr(), M,
+                                C_, eps, _stream()), "ctu_layernorm_bwd")
+
+
+def gelu(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    lib = _lib.require_device()
+    assert x.is_contiguous() and y.is_contiguous()
+    check(lib.ctu_gelu(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "ctu_gelu")
+    return y
+
+
+def gelu_backward(x: torch.Tensor, dy: torch.Tensor, dx: torch.Tensor) -> torch.Tensor:
+    lib = _lib.require_device()
+    assert x.is_contiguous() and dy.is_contiguous() and dx.is_contiguous()
+    check(lib.ctu_gelu_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), _stream()), "ctu_gelu_bwd")
+    return dx
+
+
+def pwa_fuse_backward(qkv1, qkv2, dout, dqkv1, dqkv2, dim_head: int = 32):
+    lib = _lib.require_device()
+    T, C3 = qkv1.shape
+    for t in (qkv1, qkv2, dout, dqkv1, dqkv2):
+        assert t.is_contiguous()
+    check(lib.ctu_pwa_fuse_bwd(qkv1.data_ptr(), qkv2.data_ptr(), dout.data_ptr(), dqkv1.data_ptr(), dqkv2.data_ptr(), T,
+                               C3 // 3, dim_head, _stream()), "ctu_pwa_fuse_bwd")
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor, n: Optional[int] = None) -> torch.Tensor:
+    """out[c] += sum_rows x[row, c]; x: [M, >= n] bf16/fp32 with row stride x.stride(-2); out fp32 [n]."""
+    lib = _lib.require_device()
+    N = int(n if n is not None else x.shape[-1])
+    M = x.numel() // x.shape[-1] if x.is_contiguous() else x.shape[0]
+    check(lib.ctu_colsum(x.data_ptr(), int(x.dtype == torch.float32), int(x.stride(-2)), M, N, out.data_ptr(), _stream()),
+          "ctu_colsum")
+    return out
+
+
+def cf_to_cl(src: torch.Tensor, dst: torch.Tensor, cpad: int) -> torch.Tensor:
+    """src: fp32 [B, C, X, Y, Z] contiguous -> dst: bf16 [B, X, Y, Z, ld] with channels [C, cpad) zeroed."""
+    lib = _lib.require_device()
+    assert src.is_contiguous() and src.dtype == torch.float32
+    B, C_ = src.shape[:2]
+    S = src.numel() // (B * C_)
+    check(lib.ctu_cf_to_cl(src.data_ptr(), dst.data_ptr(), B, C_, S, int(dst.stride(-2)), cpad, _stream()), "ctu_cf_to_cl")
+    return dst
+
+
+def space_to_depth(x: torch.Tensor, out: torch.Tensor, up: Tuple[int, int, int]) -> torch.Tensor:
+    """x: bf16 [B, X*ux, Y*uy, Z*uz, C] -> out: contiguous [B, X, Y, Z, ux*uy*uz*C]; up = (ux, uy, uz)."""
+    lib = _lib.require_device()
+    B, Xu, Yu, Zu, C_ = x.shape
+    ux, uy, uz = up
+    assert out.is_contiguous()
+    check(lib.ctu_space_to_depth(x.data_ptr(), int(x.stride(-2)), out.data_ptr(), B, Xu // ux, Yu // uy, Zu // uz, ux, uy,
+                                 uz, C_, _stream()), "ctu_space_to_depth")
+    return out
+
+
+def subsample_backward(dsub: torch.Tensor, dfull: torch.Tensor, stride, accumulate: bool = False) -> torch.Tensor:
+    lib = _lib.require_device()
+    B, X, Y, Z, C_ = dfull.shape
+    sx, sy, sz = stride
+    check(lib.ctu_subsample_bwd(dsub.data_ptr(), int(dsub.stride(-2)), dfull.data_ptr(), int(dfull.stride(-2)), Z, Y, X,
+                                sz, sy, sx, C_, B, 1 if accumulate else 0, _stream()), "ctu_subsample_bwd")
+    return dfull
+
+
+def im2col_cin1(x: torch.Tensor, out: torch.Tensor, *, k, s, p) -> torch.Tensor:
+    """x: fp32 [B,1,X,Y,Z]; out: bf16 contiguous [B,Xo,Yo,Zo,kpad]."""
+    lib = _lib.require_device()
+    B, c, X, Y, Z = x.shape
+    assert c == 1 and x.is_contiguous() and out.is_contiguous()
+    check(lib.ctu_im2col_cin1(x.data_ptr(), out.data_ptr(), B, X, Y, Z, k[0], k[1], k[2], s[0], s[1], s[2], p[0], p[1],
+                              p[2], out.shape[-1], _stream()), "ctu_im2col_cin1")
+    return out
+
+
+def accumulate(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst += src for [.., C] tensors with arbitrary row strides (same dtype, bf16 or fp32)."""
+    lib = _lib.require_device()
+    assert src.dtype == dst.dtype and src.shape == dst.shape
+    C_ = src.shape[-1]
+    M = src.numel() // C_
+    check(lib.ctu_accumulate(src.data_ptr(), int(src.stride(-2)), dst.data_ptr(), int(dst.stride(-2)), M, C_,
+                             int(src.dtype == torch.float32), _stream()), "ctu_accumulate")
+    return dst
+
+
+def cast_f32_bf16(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    lib = _lib.require_device()
+    C_ = src.shape[-1]
+    M = src.numel() // C_
+    check(lib.ctu_cast_f32_bf16(src.data_ptr(), int(src.stride(-2)), dst.data_ptr(), int(dst.stride(-2)), M, C_, _stream()),
+          "ctu_cast_f32_bf16")
+    return dst
+
+
+def patchify_ln_backward(img, pf: int, dtok, dgamma, dbeta, eps: float = 1e-5):
+    lib = _lib.require_device()
+    B, c, X, Y, Z = img.shape
+    check(lib.ctu_patchify_ln_bwd(img.data_ptr(), B, X, Y, Z, pf, dtok.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), eps,
+                                  _stream()), "ctu_patchify_ln_bwd")
+
+
+def attention_backward(qkv, out, dout, lse, dqkv, dq_f32, *, dim_head: int, n: int, windows: int = 0, mode: int = 0,
+                       bias_t: Optional[torch.Tensor] = None, ds_out: Optional[torch.Tensor] = None,
+                       grid: Tuple[int, int, int, int] = (1, 1, 1, 1), w: int = 6):
+    """Backward of `attention`.  dK/dV -> dqkv[:, C:], dQ accumulated into dq_f32 (fp32 [rows, C], zeroed by the caller)."""
+    lib = _lib.require_device()
+    C_ = qkv.shape[-1] // 3
+    rows = qkv.shape[0]
+    heads = C_ // dim_head
+    delta = torch.empty(rows, heads, dtype=torch.float32, device=qkv.device)
+    check(lib.ctu_attention_delta(out.data_ptr(), int(out.stride(-2)), dout.data_ptr(), int(dout.stride(-2)),
+                                  delta.data_ptr(), rows, C_, dim_head, _stream()), "ctu_attention_delta")
+    b, X, Y, Z = grid
+    check(lib.ctu_attention_bwd(qkv.data_ptr(), int(qkv.stride(-2)), C_, dim_head, dout.data_ptr(), int(dout.stride(-2)),
+                                lse.data_ptr(), delta.data_ptr(), _ptr(bias_t), dqkv.data_ptr(), int(dqkv.stride(-2)),
+                                dq_f32.data_ptr(), _ptr(ds_out), n, windows, mode, b, X, Y, Z, w, _stream()),
+          "ctu_attention_bwd")

@@ -107,9 +107,10 @@ int ctu_subsample(const void* in, int ldi, int i1, int i2, int i3, void* out, in
 /* softmax(Q K^T / sqrt(dh) + bias) V.  mode 0: ViT attention over `windows` groups of n consecutive rows
  * (vit.py:66-78); mode 1 / 2: MultiAxisAttention over the block '(h h1)' / grid '(h1 h)' partition of a
  * [batch, X, Y, Z] token grid into w^3 windows with additive relative-position bias fp32 [heads][n][n]
- * (hybrid_CTUNet.py:481-511, 559-567). */
+ * (hybrid_CTUNet.py:481-511, 559-567).  lse (fp32 [rows][heads], or NULL) receives the base-2 log-sum-exp of
+ * the scaled, biased scores of every (row, head) — what the backward pass recomputes the probabilities from. */
 int ctu_attention(const void* qkv, int ld_qkv, int C, int dim_head, void* out, int ldo, const float* bias, int n,
-                  int windows, int mode, int batch, int X, int Y, int Z, int w, void* stream);
+                  int windows, int mode, int batch, int X, int Y, int Z, int w, float* lse, void* stream);
 
 /* Conv3d with one input channel on CUDA cores: ResNet stem (resnet.py:150-155) and vit_encoder0 conv1/conv3
  * (hybrid_CTUNet.py:57-83).  x: fp32 [B][X][Y][Z]; w: fp32 [kx*ky*kz][64]; out: bf16 channels-last. */
@@ -122,6 +123,98 @@ int ctu_blend_accumulate(const float* logits0, const float* logits1, const float
 int ctu_blend_count(const float* imp, float* cnt, int r3, int r2, int r1, int X, int Y, int Z, int x0, int y0, int z0,
                     void* stream);
 int ctu_blend_normalize(const float* acc, const float* cnt, float* out, int C, long long vox, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Backward pass (training step, trainer_CTUNet.py:87-109: loss.backward() through the modules above).
+ * The reference gets these from torch autograd over cuDNN / cuBLAS; here each is an explicit kernel.
+ * Input gradients of the contractions reuse ctu_umma_gemm with transposed / tap-flipped weights.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* Weight gradient of a plain GEMM / 1x1x1 Conv3d (k=1) or a stride-1 "same" 3x3x3 Conv3d (k=3):
+ *   dw[(tap*x_c + ci)][co] += sum over voxels v of x[v + tap - pad][ci] * dy[v][co]
+ * (the transpose of the packed forward weight [n][k_total]).  tcgen05 contraction over the voxel axis with both
+ * operands MN-major; split over voxel chunks, accumulated with fp32 reductions, so dw must be zeroed (or hold a
+ * running sum) before the call.  Replaces cudnn wgrad / cuBLAS for every get_conv_layer and nn.Linear on the path. */
+typedef struct ctu_wgrad_desc {
+  const void* x;   /* bf16 [d4][d3][d2][d1][ldx], first x_c channels used; x_c % 64 == 0 */
+  const void* dy;  /* bf16 [d4][d3][d2][d1][ldy], first n channels used */
+  float* dw;       /* fp32 [k1*k2*k3*x_c][ldw], columns [0, n) accumulated */
+  int32_t x_c, ldx;
+  int32_t n, ldy;
+  int32_t ldw;
+  int32_t d1, d2, d3, d4;
+  int32_t b1, b2, b3; /* tile box, b1*b2*b3 == 128 */
+  int32_t k1, k2, k3; /* all 1 or all 3 */
+  int32_t block_n;    /* 64, 128 or 256 */
+} ctu_wgrad_desc;
+
+int ctu_umma_wgrad(const ctu_wgrad_desc* desc, void* stream);
+
+/* Backward of ctu_in_apply: out = act(IN(x) [+ res | + IN(res)]).  With g = dout * act'(out):
+ *   dx = rstd_x * (g - mean(g) - xhat * mean(g*xhat)); dres = g (res_mode 1) or the same formula with the
+ *   residual's statistics (res_mode 2).  ctu_in_bwd_stats accumulates sums[b][c] = (sum g, sum g*xhat, sum g*rhat, -)
+ *   as fp64 [B][C][4] (zeroed by the caller; pass rstats == NULL unless res_mode == 2); ctu_in_bwd_apply consumes it. */
+int ctu_in_bwd_stats(const void* dout, int ldd, const void* out, int ldo, const void* x, int ldx, const double* xstats,
+                     int xs_ld, const void* res, int ldr, const double* rstats, int rs_ld, int B, long long S, int C,
+                     float eps, int act, float slope, double* sums, void* stream);
+int ctu_in_bwd_apply(const void* dout, int ldd, const void* out, int ldo, const void* x, int ldx, const double* xstats,
+                     int xs_ld, const void* res, int ldr, const double* rstats, int rs_ld, int res_mode, int B,
+                     long long S, int C, float eps, int act, float slope, const double* sums, void* dx, int lddx,
+                     void* dres, int lddr, void* stream);
+
+/* nn.LayerNorm backward.  dy: bf16 [M][C].  dx = LN'(dy) (+ dx_in, the gradient already flowing along the residual
+ * stream, fp32 or bf16) written as fp32 and/or bf16; dgamma / dbeta fp32 [C] are accumulated. */
+int ctu_layernorm_bwd(const void* x, int x_is_f32, long long ldx, const float* gamma, const void* dy, long long ldd,
+                      const void* dx_in, int dxin_is_f32, long long ld_in, float* dx_f32, long long ld_f, void* dx_bf16,
+                      long long ld_b, float* dgamma, float* dbeta, long long M, int C, float eps, void* stream);
+
+/* Exact-erf GELU on contiguous bf16 (n % 8 == 0) and its derivative: dx = dy * gelu'(x). */
+int ctu_gelu(const void* x, void* y, long long n, void* stream);
+int ctu_gelu_bwd(const void* x, const void* dy, void* dx, long long n, void* stream);
+
+/* Backward of ctu_pwa_fuse: dqkv1 / dqkv2 bf16 [T][3C] from dout bf16 [T][C]. */
+int ctu_pwa_fuse_bwd(const void* qkv1, const void* qkv2, const void* dout, void* dqkv1, void* dqkv2, long long T, int C,
+                     int dim_head, void* stream);
+
+/* out[c] += sum over the M rows of x[row][c], x bf16 or fp32 [M][ldx], N columns (bias gradients, position-embedding
+ * gradient, relative-position-bias gradient over windows). */
+int ctu_colsum(const void* x, int x_is_f32, long long ldx, long long M, long long N, float* out, void* stream);
+
+/* NCDHW fp32 [B][C][S] -> channels-last bf16 [B][S][ldd] with channels [C, cpad) zero (logit gradients). */
+int ctu_cf_to_cl(const float* src, void* dst, int B, int C, long long S, int ldd, int cpad, void* stream);
+
+/* in [B][X*u3][Y*u2][Z*u1][ldi] (C channels) -> out [B][X][Y][Z][u3*u2*u1*C], column (sub*C + c),
+ * sub = (a3*u2 + a2)*u1 + a1: gradient of a kernel==stride ConvTranspose3d / pixel shuffle as a GEMM output. */
+int ctu_space_to_depth(const void* in, int ldi, void* out, int B, int X, int Y, int Z, int u3, int u2, int u1, int C,
+                       void* stream);
+
+/* Backward of ctu_subsample: dfull[b, x*s3, y*s2, z*s1, :] (+)= dsub[b,x,y,z,:]; without `accumulate` every other
+ * position of dfull is zeroed. */
+int ctu_subsample_bwd(const void* dsub, int lds, void* dfull, int ldf, int i1, int i2, int i3, int s1, int s2, int s3,
+                      int C, int B, int accumulate, void* stream);
+
+/* im2col of a single-channel fp32 volume: out bf16 [B][Xo][Yo][Zo][kpad], column = tap (x-major), zero padded — the
+ * activation operand of ctu_umma_wgrad for the C_in = 1 convolutions (resnet.py:150-155; hybrid_CTUNet.py:57-83). */
+int ctu_im2col_cin1(const float* img, void* out, int B, int X, int Y, int Z, int kx, int ky, int kz, int sx, int sy,
+                    int sz, int px, int py, int pz, int kpad, void* stream);
+
+/* dst[row][0..C) += src[row][0..C) (bf16 or fp32 rows); dst(bf16) = src(fp32). */
+int ctu_accumulate(const void* src, long long lds, void* dst, long long ldd, long long M, int C, int is_f32, void* stream);
+int ctu_cast_f32_bf16(const float* src, long long lds, void* dst, long long ldd, long long M, int C, void* stream);
+
+/* dgamma / dbeta (fp32 [256*pf], accumulated) of the LayerNorm fused into ctu_patchify_ln. */
+int ctu_patchify_ln_bwd(const float* img, int B, int X, int Y, int Z, int pf, const void* dtok, float* dgamma,
+                        float* dbeta, float eps, void* stream);
+
+/* Attention backward.  ctu_attention_delta: delta[row][head] = sum_d dO*O.  ctu_attention_bwd: dK, dV written to
+ * dqkv (bf16 [rows][3C] = dq|dk|dv), dQ ACCUMULATED into dq_f32 (fp32 [rows][C], zeroed by the caller); biasT is the
+ * additive bias indexed [head][key][query]; ds_out (bf16 [windows][heads][n][n], [key][query], or NULL) receives
+ * dScores for the relative-position-bias gradient. */
+int ctu_attention_delta(const void* o, long long ldo, const void* dout, long long ldd, float* delta, long long rows, int C,
+                        int dim_head, void* stream);
+int ctu_attention_bwd(const void* qkv, int ld_qkv, int C, int dim_head, const void* dout, int ldd, const float* lse,
+                      const float* delta, const float* biasT, void* dqkv, int ld_dqkv, float* dq_f32, void* ds_out, int n,
+                      int windows, int mode, int batch, int X, int Y, int Z, int w, void* stream);
 
 /* Number of kernels this library has launched since load (bench.py's "gpu_launches"). */
 int64_t ctu_launch_count(void);

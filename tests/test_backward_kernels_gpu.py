@@ -1,0 +1,332 @@
+"""Kernel-level parity of the backward-pass kernels (ctu_umma_wgrad, ctu_in_bwd_*, ctu_layernorm_bwd, ctu_gelu*,
+ctu_pwa_fuse_bwd, ctu_attention_bwd, layout helpers) against torch fp32 autograd of the same op on the same
+bf16-rounded inputs.  Tolerances: bf16 outputs rel-L2 <= 1e-2 (north_star bf16 tolerance), fp32-accumulated weight
+gradients <= 2e-3 (inputs are identical bf16 values; only the summation order differs)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+@pytest.fixture(autouse=True)
+def _strict_fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def rbf(*shape, scale=1.0):
+    return (torch.randn(*shape, device="cuda") * scale).to(BF)
+
+
+# ---------------------------------------------------------------------------------------------- tcgen05 wgrad
+@pytest.mark.parametrize("M,K,N", [(1000, 128, 64), (864, 768, 2304), (5000, 64, 128), (777, 192, 320), (128, 64, 64),
+                                   (40000, 128, 512), (300, 1024, 256)])
+def test_wgrad_plain(M, K, N):
+    from hybrid_ctunet_b200 import ops
+    torch.manual_seed(M + K + N)
+    x, dy = rbf(M, K), rbf(M, N)
+    dw = torch.zeros(K, N, device="cuda")
+    ops.wgrad(x, dy, dw, dims=(M, 1, 1, 1))
+    ref = x.float().t() @ dy.float()
+    assert rel(dw, ref) < 2e-3
+    ops.wgrad(x, dy, dw, dims=(M, 1, 1, 1))  # accumulates
+    assert rel(dw, 2 * ref) < 2e-3
+
+
+def test_wgrad_strided_operands_and_padded_columns():
+    """x / dy are column slices of wider buffers (concat-by-offset), dy has n < ldy, dw has ldw > n."""
+    from hybrid_ctunet_b200 import ops
+    torch.manual_seed(3)
+    M = 3000
+    xb, dyb = rbf(M, 256), rbf(M, 64)
+    x, dy = xb[:, 64:192], dyb[:, :16]
+    dw = torch.zeros(128, 24, device="cuda")
+    ops.wgrad(x, dy, dw, dims=(M, 1, 1, 1), n=16)
+    ref = x.float().t() @ dy.float()
+    assert rel(dw[:, :16], ref) < 2e-3 and float(dw[:, 16:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,X,Y,Z,Ci,Co", [(2, 8, 12, 16, 64, 64), (1, 6, 6, 12, 128, 128), (1, 5, 7, 9, 64, 256),
+                                           (2, 12, 12, 24, 64, 128), (1, 4, 4, 8, 256, 256)])
+def test_wgrad_conv3(B, X, Y, Z, Ci, Co):
+    from hybrid_ctunet_b200 import ops
+    torch.manual_seed(B * X + Ci + Co)
+    x, dy = rbf(B, X, Y, Z, Ci), rbf(B, X, Y, Z, Co)
+    dw = torch.zeros(27 * Ci, Co, device="cuda")
+    ops.wgrad(x, dy, dw, dims=(Z, Y, X, B), ksize=3)
+    w = torch.zeros(Co, Ci, 3, 3, 3, device="cuda", requires_grad=True)
+    y = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w, padding=1)
+    y.backward(dy.float().permute(0, 4, 1, 2, 3))
+    ref = w.grad.permute(2, 3, 4, 1, 0).reshape(27 * Ci, Co)
+    assert rel(dw, ref) < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------- InstanceNorm backward
+def _in_ref(x, res, mode):
+    xn = F.instance_norm(x.permute(0, 4, 1, 2, 3), eps=1e-5)
+    if mode == 1:
+        xn = xn + res.permute(0, 4, 1, 2, 3)
+    elif mode == 2:
+        xn = xn + F.instance_norm(res.permute(0, 4, 1, 2, 3), eps=1e-5)
+    return F.leaky_relu(xn, 0.01).permute(0, 2, 3, 4, 1)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("C", [64, 128, 512])
+def test_in_backward(mode, C):
+    from hybrid_ctunet_b200 import ops
+    torch.manual_seed(C + mode)
+    B, X, Y, Z = 2, 6, 10, 12
+    x = rbf(B, X, Y, Z, C) + 0.3
+    res = rbf(B, X, Y, Z, C)
+    dout = rbf(B, X, Y, Z, C)
+    st = torch.zeros(B, C, 2, dtype=torch.float64, device="cuda")
+    rst = torch.zeros(B, C, 2, dtype=torch.float64, device="cuda")
+    ops.in_stats(x, st)
+    ops.in_stats(res, rst)
+    out = torch.empty_like(x)
+    ops.in_apply(x, st, out, res=res if mode else None, rstats=rst if mode == 2 else None, act=True)
+    dx, dres = torch.empty_like(x), torch.empty_like(x)
+    ops.in_backward(dout, out, x, st, dx, res=res if mode else None, rstats=rst if mode == 2 else None,
+                    dres=dres if mode else None)
+    xf, rf = x.float().requires_grad_(), res.float().requires_grad_()
+    ref = _in_ref(xf, rf, mode)
+    assert rel(out, ref) < 1e-2
+    ref.backward(dout.float())
+    assert rel(dx, xf.grad) < 1e-2
+    if mode:
+        assert rel(dres, rf.grad) < 1e-2
+
+
+# ---------------------------------------------------------------------------------------------- LayerNorm backward
+@pytest.mark.parametrize("C,xf32", [(128, False), (256, True), (768, True), (512, False), (1024, False)])
+def test_layernorm_backward(C, xf32):
+    from hybrid_ctunet_b200 import ops
+    torch.manual_seed(C)
+    M = 1234
+    x = torch.randn(M, C, device="cuda") * 2 + 0.5
+    if not xf32:
+        x = x.to(BF)
+    gamma = torch.randn(C, device="cuda")
+    dy = rbf(M, C)
+    dx_in = torch.randn(M, C, device="cuda")
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx32, dx16 = torch.empty(M, C, device="cuda"), torch.empty(M, C, device="cuda", dtype=BF)
+    ops.layernorm_backward(x, gamma, dy, dg, db, dx_in=dx_in, dx_f32=dx32, dx_bf16=dx16)
+    xr = x.float().requires_grad_()
+    gr = gamma.clone().requires_grad_()
+    br = torch.zeros(C, device="cuda", requires_grad=True)
+    F.layer_norm(xr, (C,), gr, br, 1e-5).backward(dy.float())
+    assert rel(dx32, xr.grad + dx_in) < 1e-4
+    assert rel(dx16, xr.grad + dx_in) < 1e-2
+    assert rel(dg, gr.grad) < 1e-3 and rel(db, br.grad) < 1e-3
+
+
+def test_gelu_forward_backward():
+    from hybrid_ctunet_b200 import ops
+    torch.manual_seed(0)
+    x, dy = rbf(1000, 256, scale=2.0), rbf(1000, 256)
+    y, dx = torch.empty_like(x), torch.empty_like(x)
+    ops.gelu(x, y)
+    ops.gelu_backward(x, dy, dx)
+    xr = x.float().requires_grad_()
+    ref = F.gelu(xr)
+    ref.backward(dy.float())
+    assert rel(y, ref) < 1e-2 and rel(dx, xr.grad) < 1e-2
+
+
+def test_pwa_fuse_backward():
+    from hybrid_ctunet_b200 import ops
+    torch.manual_seed(1)
+    T, C, dh = 3000, 128, 32
+    q1, q2, dout = rbf(T, 3 * C), rbf(T, 3 * C), rbf(T, C)
+    d1, d2 = torch.empty_like(q1), torch.empty_like(q2)
+    ops.pwa_fuse_backward(q1, q2, dout, d1, d2)
+    a, b = q1.float().requires_grad_(), q2.float().requires_grad_()
+    H = C // dh
+    qa, ka, va = [t.reshape(T, H, dh) for t in a.chunk(3, -1)]
+    qb, kb, vb = [t.reshape(T, H, dh) for t in b.chunk(3, -1)]
+    dots = torch.stack(((qb * ka).sum(-1), (qa * kb).sum(-1)), -1) * dh ** -0.5
+    att = dots.softmax(-1)
+    out = (att[..., 0:1] * va + att[..., 1:2] * vb).reshape(T, C)
+    out.backward(dout.float())
+    assert rel(d1, a.grad) < 1e-2 and rel(d2, b.grad) < 1e-2
+
+
+# ---------------------------------------------------------------------------------------------- helpers
+def test_colsum_cast_accumulate():
+    from hybrid_ctunet_b200 import ops
+    torch.manual_seed(2)
+    x = rbf(5000, 192)
+    out = torch.zeros(192, device="cuda")
+    ops.colsum(x, out)
+    assert rel(out, x.float().sum(0)) < 1e-4
+    xf = torch.randn(7, 46656, device="cuda")
+    of = torch.zeros(46656, device="cuda")
+    ops.colsum(xf, of)
+    assert rel(of, xf.sum(0)) < 1e-5
+    wide = rbf(300, 256)
+    o2 = torch.zeros(64, device="cuda")
+    ops.colsum(wide[:, 64:128], o2, n=64)
+    assert rel(o2, wide[:, 64:128].float().sum(0)) < 1e-4
+    a, b = rbf(400, 128), rbf(400, 256)
+    ref = a.float() + b[:, 128:].float()
+    ops.accumulate(a, b[:, 128:])
+    assert rel(b[:, 128:], ref) < 1e-2
+    f1, f2 = torch.randn(100, 64, device="cuda"), torch.randn(100, 64, device="cuda")
+    ref = f1 + f2
+    ops.accumulate(f1, f2)
+    assert torch.equal(f2, ref)
+    dst = torch.empty(100, 64, device="cuda", dtype=BF)
+    ops.cast_f32_bf16(f1, dst)
+    assert torch.equal(dst, f1.to(BF))
+
+
+def test_cf_to_cl():
+    from hybrid_ctunet_b200 import ops
+    torch.manual_seed(4)
+    src = torch.randn(2, 14, 5, 7, 9, device="cuda")
+    dst = torch.full((2, 5, 7, 9, 64), 7.0, device="cuda", dtype=BF)
+    ops.cf_to_cl(src, dst, 64)
+    assert torch.equal(dst[..., :14], src.permute(0, 2, 3, 4, 1).to(BF)) and float(dst[..., 14:].abs().max()) == 0.0
+
+
+def test_space_to_depth_matches_forward_up_gemm_layout():
+    from hybrid_ctunet_b200 import ops
+    torch.manual_seed(5)
+    B, X, Y, Z, C = 2, 3, 4, 5, 64
+    for up in ((2, 2, 2), (2, 2, 1)):
+        ux, uy, uz = up
+        x = rbf(B, X * ux, Y * uy, Z * uz, C)
+        out = torch.empty(B, X, Y, Z, ux * uy * uz * C, device="cuda", dtype=BF)
+        ops.space_to_depth(x, out, up)
+        ref = x.reshape(B, X, ux, Y, uy, Z, uz, C).permute(0, 1, 3, 5, 2, 4, 6, 7).reshape(B, X, Y, Z, -1)
+        assert torch.equal(out, ref)
+
+
+def test_subsample_backward():
+    from hybrid_ctunet_b200 import ops
+    torch.manual_seed(6)
+    B, X, Y, Z, C = 2, 7, 8, 9, 64
+    for s in ((2, 2, 2), (2, 2, 1)):
+        sub = rbf(B, -(-X // s[0]), -(-Y // s[1]), -(-Z // s[2]), C)
+        full = rbf(B, X, Y, Z, C)
+        ref0 = torch.zeros_like(full)
+        ref0[:, ::s[0], ::s[1], ::s[2]] = sub
+        ref1 = (full.float() + ref0.float()).to(BF)
+        out = torch.empty_like(full)
+        ops.subsample_backward(sub, out, s)
+        assert torch.equal(out, ref0)
+        ops.subsample_backward(sub, full, s, accumulate=True)
+        assert torch.equal(full, ref1)
+
+
+def test_im2col_cin1_wgrad_matches_conv_weight_grad():
+    from hybrid_ctunet_b200 import ops
+    torch.manual_seed(7)
+    B, X, Y, Z = 1, 12, 10, 14
+    img = torch.randn(B, 1, X, Y, Z, device="cuda")
+    for k, s, p, kpad in (((7, 7, 7), (2, 2, 1), (3, 3, 3), 384), ((3, 3, 3), (1, 1, 1), (1, 1, 1), 64),
+                          ((1, 1, 1), (1, 1, 1), (0, 0, 0), 64)):
+        Xo, Yo, Zo = [(d + 2 * pp - kk) // ss + 1 for d, kk, ss, pp in zip((X, Y, Z), k, s, p)]
+        col = torch.empty(B, Xo, Yo, Zo, kpad, device="cuda", dtype=BF)
+        ops.im2col_cin1(img, col, k=k, s=s, p=p)
+        dy = rbf(B, Xo, Yo, Zo, 64)
+        dw = torch.zeros(kpad, 64, device="cuda")
+        ops.wgrad(col, dy, dw, dims=(Zo, Yo, Xo, B))
+        w = torch.zeros(64, 1, *k, device="cuda", requires_grad=True)
+        F.conv3d(img.to(BF).float(), w, stride=s, padding=p).backward(dy.float().permute(0, 4, 1, 2, 3))
+        taps = k[0] * k[1] * k[2]
+        assert rel(dw[:taps], w.grad.reshape(64, taps).t()) < 2e-3
+        assert float(dw[taps:].abs().max()) == 0.0
+
+
+def test_patchify_ln_backward():
+    from hybrid_ctunet_b200 import ops
+    from einops import rearrange
+    torch.manual_seed(8)
+    B, X, Y, Z, pf = 2, 32, 32, 16, 8
+    img = torch.randn(B, 1, X, Y, Z, device="cuda")
+    tokens = B * (X // 16) * (Y // 16) * (Z // pf)
+    dtok = rbf(tokens, 256 * pf)
+    dg, db = torch.zeros(256 * pf, device="cuda"), torch.zeros(256 * pf, device="cuda")
+    ops.patchify_ln_backward(img, pf, dtok, dg, db)
+    g = torch.ones(256 * pf, device="cuda", requires_grad=True)
+    b = torch.zeros(256 * pf, device="cuda", requires_grad=True)
+    t = rearrange(img, "b c (h p1) (w p2) (f pf) -> (b h w f) (p1 p2 pf c)", p1=16, p2=16, pf=pf)
+    F.layer_norm(t, (256 * pf,), g, b, 1e-5).backward(dtok.float())
+    assert rel(dg, g.grad) < 1e-3 and rel(db, b.grad) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------- attention backward
+def _window_rows(mode, B, X, Y, Z, w):
+    """row index table [windows, w^3] of the block / grid partition (hybrid_CTUNet.py:559-567)."""
+    idx = torch.arange(B * X * Y * Z).reshape(B, X, Y, Z)
+    nx, ny, nz = X // w, Y // w, Z // w
+    if mode == 1:
+        t = idx.reshape(B, nx, w, ny, w, nz, w).permute(0, 1, 3, 5, 2, 4, 6)
+    else:
+        t = idx.reshape(B, w, nx, w, ny, w, nz).permute(0, 2, 4, 6, 1, 3, 5)
+    return t.reshape(-1, w ** 3)
+
+
+@pytest.mark.parametrize("mode,D,heads", [(0, 64, 12), (1, 32, 8), (2, 32, 4), (0, 32, 3)])
+def test_attention_backward(mode, D, heads):
+    from hybrid_ctunet_b200 import ops
+    torch.manual_seed(10 + mode + D)
+    C = D * heads
+    if mode == 0:
+        B, n = 2, 432 if D == 64 else 100
+        rows = B * n
+        tbl = torch.arange(rows).reshape(B, n)
+        grid, bias = (1, 1, 1, 1), None
+    else:
+        B, X, Y, Z, w = 2, 6, 12, 12, 6
+        n, rows = 216, B * X * Y * Z
+        tbl = _window_rows(mode, B, X, Y, Z, w)
+        grid = (B, X, Y, Z)
+        bias = torch.randn(heads, n, n, device="cuda")
+    qkv = rbf(rows, 3 * C, scale=0.7)
+    dout = rbf(rows, C)
+    out = torch.empty(rows, C, device="cuda", dtype=BF)
+    lse = torch.empty(rows, heads, device="cuda")
+    ops.attention(qkv, out, dim_head=D, n=n, windows=tbl.shape[0], mode=mode, bias=bias, grid=grid, lse=lse)
+    dqkv = torch.zeros(rows, 3 * C, device="cuda", dtype=BF)
+    dq = torch.zeros(rows, C, device="cuda")
+    ds = torch.zeros(tbl.shape[0], heads, n, n, device="cuda", dtype=BF) if bias is not None else None
+    bias_t = bias.transpose(1, 2).contiguous() if bias is not None else None
+    ops.attention_backward(qkv, out, dout, lse, dqkv, dq, dim_head=D, n=n, windows=tbl.shape[0], mode=mode,
+                           bias_t=bias_t, ds_out=ds, grid=grid)
+    # torch reference on the same bf16 inputs
+    qr = qkv.float().requires_grad_()
+    br = bias.clone().requires_grad_() if bias is not None else None
+    t = tbl.cuda()
+    g = qr[t]                                                    # [win, n, 3C]
+    q, k, v = [a.reshape(-1, n, heads, D).transpose(1, 2) for a in g.chunk(3, -1)]
+    sc = q @ k.transpose(-1, -2) * D ** -0.5
+    if br is not None:
+        sc = sc + br
+    o = (sc.softmax(-1) @ v).transpose(1, 2).reshape(-1, n, C)
+    ref_out = torch.zeros(rows, C, device="cuda").index_put((t.reshape(-1),), o.reshape(-1, C))
+    assert rel(out, ref_out) < 1e-2
+    ref_lse = torch.logsumexp(sc, -1) / math.log(2.0)            # [win, heads, n]
+    got_lse = lse[t].permute(0, 2, 1)
+    assert (got_lse - ref_lse).abs().max().item() < 2e-2
+    ref_out.backward(dout.float())
+    assert rel(dq, qr.grad[:, :C]) < 1.5e-2
+    assert rel(dqkv[:, C:2 * C], qr.grad[:, C:2 * C]) < 1.5e-2
+    assert rel(dqkv[:, 2 * C:], qr.grad[:, 2 * C:]) < 1.5e-2
+    if bias is not None:
+        dbias_t = torch.zeros(heads * n * n, device="cuda")
+        ops.colsum(ds.reshape(tbl.shape[0], -1), dbias_t)
+        assert rel(dbias_t.reshape(heads, n, n).transpose(1, 2), br.grad) < 2e-2
