@@ -27,7 +27,7 @@ SIGS = {
     "ctu_space_to_depth": (P, I, P, I, I, I, I, I, I, I, I, P),
     "ctu_subsample_bwd": (P, I, P, I, I, I, I, I, I, I, I, I, I, P),
     "ctu_im2col_cin1": (P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, I, P),
-    "ctu_accumulate": (P, L, P, L, L, I, I, P),
+    "ctu_accumulate": (P, I, L, P, I, L, L, I, P),
     "ctu_cast_f32_bf16": (P, L, P, L, L, I, P),
     "ctu_patchify_ln_bwd": (P, I, I, I, I, I, P, P, P, F, P),
     "ctu_attention_delta": (P, L, P, L, P, L, I, I, P),

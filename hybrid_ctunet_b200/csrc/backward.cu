@@ -547,29 +547,25 @@ __global__ void __launch_bounds__(256) im2col_cin1_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// dst[row][0..C) += src[row][0..C)   (gradient accumulation where an activation has several consumers)
-template <typename T>
-__global__ void __launch_bounds__(256) accumulate_kernel(const T* __restrict__ src, long long lds, T* __restrict__ dst,
+// dst[row][0..C) += src[row][0..C)   (gradient accumulation where an activation has several consumers);
+// src / dst are bf16 or fp32 independently (bf16 branch gradients joining an fp32 residual-stream gradient).
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) accumulate_kernel(const TS* __restrict__ src, long long lds, TD* __restrict__ dst,
                                                          long long ldd, long long M, int C) {
-  constexpr int V = sizeof(T) == 2 ? 8 : 4;
-  const int tpr = C / V;
+  const int tpr = C / 8;
   const long long total = M * tpr;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / tpr;
     const int cv = (int)(i - r * tpr);
-    if constexpr (sizeof(T) == 2) {
-      float a[8], b[8];
-      ld8(reinterpret_cast<const __nv_bfloat16*>(src) + r * lds + cv * 8, a);
-      ld8(reinterpret_cast<const __nv_bfloat16*>(dst) + r * ldd + cv * 8, b);
+    float a[8], b[8];
+    if constexpr (sizeof(TS) == 2) ld8(reinterpret_cast<const __nv_bfloat16*>(src) + r * lds + cv * 8, a);
+    else ld8f(reinterpret_cast<const float*>(src) + r * lds + cv * 8, a);
+    if constexpr (sizeof(TD) == 2) ld8(reinterpret_cast<const __nv_bfloat16*>(dst) + r * ldd + cv * 8, b);
+    else ld8f(reinterpret_cast<const float*>(dst) + r * ldd + cv * 8, b);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] += b[j];
-      st8(reinterpret_cast<__nv_bfloat16*>(dst) + r * ldd + cv * 8, a);
-    } else {
-      const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + r * lds + cv * 4);
-      float4 b = *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + r * ldd + cv * 4);
-      b.x += a.x; b.y += a.y; b.z += a.z; b.w += a.w;
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + r * ldd + cv * 4) = b;
-    }
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    if constexpr (sizeof(TD) == 2) st8(reinterpret_cast<__nv_bfloat16*>(dst) + r * ldd + cv * 8, a);
+    else st8f(reinterpret_cast<float*>(dst) + r * ldd + cv * 8, a);
   }
 }
 
@@ -833,13 +829,15 @@ extern "C" int ctu_im2col_cin1(const float* img, void* out, int B, int X, int Y,
   return (int)cudaGetLastError();
 }
 
-extern "C" int ctu_accumulate(const void* src, long long lds, void* dst, long long ldd, long long M, int C, int is_f32,
-                              void* stream) {
-  const int V = is_f32 ? 4 : 8;
-  if (!src || !dst || M <= 0 || C <= 0 || C % V || lds % V || ldd % V) return CTU_E_BADARG;
-  const int grid = bw_grid(M * (C / V), 256);
-  if (is_f32) accumulate_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, lds, (float*)dst, ldd, M, C);
-  else accumulate_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, lds, (bf16*)dst, ldd, M, C);
+extern "C" int ctu_accumulate(const void* src, int src_is_f32, long long lds, void* dst, int dst_is_f32, long long ldd,
+                              long long M, int C, void* stream) {
+  if (!src || !dst || M <= 0 || C <= 0 || C % 8 || lds % (src_is_f32 ? 4 : 8) || ldd % (dst_is_f32 ? 4 : 8)) return CTU_E_BADARG;
+  const int grid = bw_grid(M * (C / 8), 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (src_is_f32 && dst_is_f32) accumulate_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, M, C);
+  else if (src_is_f32) accumulate_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, lds, (bf16*)dst, ldd, M, C);
+  else if (dst_is_f32) accumulate_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, lds, (float*)dst, ldd, M, C);
+  else accumulate_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, lds, (bf16*)dst, ldd, M, C);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -1,4 +1,4 @@
-"""Forward engine of the CTUNet path on the sm_100a kernels.
+"""Forward / backward engine of the CTUNet path on the sm_100a kernels.
 
 Everything between the module boundary (fp32 NCDHW in, fp32 NCDHW logits out) runs here on channels-last bf16
 activations; the einops rearranges of the reference (window / grid partition, proj_feat, pixel shuffle, token
@@ -6,22 +6,25 @@ activations; the einops rearranges of the reference (window / grid partition, pr
 
 Reference call graph this engine restates (hybrid_CTUNet.py:817-857): vit -> vit_encoder0 -> vit_encoder ->
 vit_decoder0 -> heads; convnet -> res_decoder3..0 -> heads.  Block functions cite the reference per function.
+
+Training (trainer_CTUNet.py:87-109): with `Engine.tape` set, every primitive records a closure that computes its
+input / parameter gradients with the backward kernels (ctu_umma_wgrad, dgrad through ctu_umma_gemm with transposed
+weights, ctu_in_bwd_*, ctu_layernorm_bwd, ctu_attention_bwd, ...); `Engine.backward` replays the closures in
+reverse.  Activation gradients are bf16 channels-last (fp32 along the fp32 token residual streams), weight
+gradients accumulate in fp32.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 
 from . import ops
-from .ops import ACT_GELU, OUT_BF16, OUT_F32, OUT_F32_CF, PackedWeight
+from .ops import ACT_GELU, ACT_NONE, OUT_BF16, OUT_F32, OUT_F32_CF, PackedWeight
 
 DS_STRIDE = ((2, 2, 1), (2, 2, 2), (2, 2, 2), (2, 2, 2))
 BF16 = torch.bfloat16
-
-
-def _pad_to(v: int, m: int) -> int:
-    return -(-v // m) * m
+F32 = torch.float32
 
 
 def rel_pos_index(w: int) -> torch.Tensor:
@@ -32,8 +35,13 @@ def rel_pos_index(w: int) -> torch.Tensor:
     return (rel * torch.tensor([(2 * w - 1) ** 2, 2 * w - 1, 1])).sum(-1)
 
 
+def _pad64(v: int) -> int:
+    return max(v, 64)
+
+
 class WeightCache:
-    """bf16 kernel-layout copies of the module's fp32 parameters, refreshed when a parameter changes."""
+    """bf16 kernel-layout copies of the module's fp32 parameters (forward and transposed / tap-flipped for the
+    input-gradient GEMMs), refreshed when a parameter changes."""
 
     def __init__(self, params: Dict[str, torch.Tensor]):
         self.params = params
@@ -50,6 +58,59 @@ class WeightCache:
         self._cache[key] = (tag, val)
         return val
 
+    # -- generic access by (kind, name, extra): forward packing and the packing of the dgrad GEMM
+    def get(self, kind: str, name: str, extra=None) -> PackedWeight:
+        if kind == "lin":
+            return self.linear(name, bias=bool(extra))
+        if kind == "conv1":
+            return self.conv1(name, bias=bool(extra))
+        if kind == "conv3":
+            return self.conv3(name)
+        if kind == "convt":
+            return self.convt(name)
+        if kind == "ps":
+            return self.pixel_shuffle(name, extra)
+        raise KeyError(kind)
+
+    def get_t(self, kind: str, name: str, extra=None) -> PackedWeight:
+        """Weight of the input-gradient contraction dA = dOut (*) W^T."""
+        if kind == "lin":
+            def build(w, b=None):
+                n, k = w.shape
+                wt = w.t()
+                if b is not None and n < 64:  # heads: 14 logits -> the 64-channel padded gradient
+                    wt = torch.zeros(k, 64, device=w.device, dtype=w.dtype)
+                    wt[:, :n] = w.t()
+                return ops.pack_matrix(wt)
+            names = [name + ".weight"] + ([name + ".bias"] if extra else [])
+            return self._get("linT:" + name, names, build)
+        if kind == "conv1":
+            def build(w, b=None):
+                co, ci = w.shape[:2]
+                cop, cip = _pad64(co), _pad64(ci)
+                wt = torch.zeros(cip, cop, device=w.device, dtype=w.dtype)
+                wt[:ci, :co] = w.reshape(co, ci).t()
+                return ops.pack_matrix(wt)
+            names = [name + ".weight"] + ([name + ".bias"] if extra else [])
+            return self._get("c1T:" + name, names, build)
+        if kind == "conv3":
+            def build(w):
+                co, ci = w.shape[:2]
+                cop, cip = _pad64(co), _pad64(ci)
+                wp = torch.zeros(cip, 3, 3, 3, cop, device=w.device, dtype=w.dtype)
+                wp[:ci, ..., :co] = w.flip(2, 3, 4).permute(1, 2, 3, 4, 0)
+                return ops.pack_matrix(wp.reshape(cip, 27 * cop), ksize=3, a_c=cop)
+            return self._get("c3T:" + name, [name + ".weight"], build)
+        if kind == "convt":
+            def build(w):
+                ci, co, kx, ky, kz = w.shape
+                return ops.pack_matrix(w.permute(2, 3, 4, 1, 0).reshape(kx * ky * kz * co, ci).t())
+            return self._get("ctT:" + name, [name + ".weight"], build)
+        if kind == "ps":
+            return self._get("psT:" + name, [name + ".weight", name + ".bias"],
+                             lambda w, b: ops.pack_matrix(self._ps_big(w, extra).t()))
+        raise KeyError(kind)
+
     # -- nn.Linear [N, K] (+bias)
     def linear(self, name: str, bias: bool = True, block_n: Optional[int] = None) -> PackedWeight:
         names = [name + ".weight"] + ([name + ".bias"] if bias else [])
@@ -64,7 +125,7 @@ class WeightCache:
             co, ci = w.shape[:2]
             w2 = w.reshape(co, ci)
             if b is None:  # feature convs: pad to the 64-channel granularity of the activation buffers
-                cop, cip = max(co, 64), max(ci, 64)
+                cop, cip = _pad64(co), _pad64(ci)
                 if (cop, cip) != (co, ci):
                     wp = torch.zeros(cop, cip, device=w.device, dtype=w.dtype)
                     wp[:co, :ci] = w2
@@ -76,7 +137,7 @@ class WeightCache:
     def conv3(self, name: str) -> PackedWeight:
         def build(w):
             co, ci = w.shape[:2]
-            cop, cip = max(co, 64), max(ci, 64)
+            cop, cip = _pad64(co), _pad64(ci)
             wp = torch.zeros(cop, 3, 3, 3, cip, device=w.device, dtype=w.dtype)
             wp[:co, ..., :ci] = w.permute(0, 2, 3, 4, 1)
             return ops.pack_matrix(wp.reshape(cop, 27 * cip), ksize=3, a_c=cip)
@@ -90,17 +151,23 @@ class WeightCache:
             return ops.pack_matrix(w2, block_n=64 if co % 128 else 128, convt=(co, kz, ky, kx))
         return self._get("ct:" + name, [name + ".weight"], build)
 
+    @staticmethod
+    def _ps_big(w, factor):
+        co, corg = w.shape
+        k3 = factor[0] * factor[1] * factor[2]
+        big = torch.zeros(k3, co, corg, k3, device=w.device, dtype=w.dtype)
+        for s in range(k3):
+            big[s, :, :, s] = w
+        return big.reshape(k3 * co, corg * k3)
+
     # -- PixelShuffle + Linear (hybrid_CTUNet.py:404-432) as a transposed-conv-shaped GEMM
     def pixel_shuffle(self, name: str, factor) -> PackedWeight:
         def build(w, b):
-            co, corg = w.shape
+            co = w.shape[0]
             fx, fy, fz = factor
             k3 = fx * fy * fz
-            big = torch.zeros(k3, co, corg, k3, device=w.device, dtype=w.dtype)
-            for s in range(k3):
-                big[s, :, :, s] = w
-            big = big.reshape(k3 * co, corg * k3)
-            return ops.pack_matrix(big, bias=b.repeat(k3), block_n=64 if co % 128 else 128, convt=(co, fz, fy, fx))
+            return ops.pack_matrix(self._ps_big(w, factor), bias=b.repeat(k3), block_n=64 if co % 128 else 128,
+                                   convt=(co, fz, fy, fx))
         return self._get("ps:" + name, [name + ".weight", name + ".bias"], build)
 
     # -- single-input-channel convs on CUDA cores: fp32 [taps, 64]
@@ -114,12 +181,18 @@ class WeightCache:
             return emb[idx].permute(2, 0, 1).contiguous().float()
         return self._get("rb:" + name, [name + ".weight"], build)
 
+    def rel_bias_t(self, name: str, w: int = 6) -> torch.Tensor:
+        """[heads][key][query] copy for the attention backward kernel."""
+        return self._get("rbT:" + name, [name + ".weight"],
+                         lambda emb: emb[rel_pos_index(w).to(emb.device)].permute(2, 1, 0).contiguous().float())
+
     def f32(self, name: str) -> torch.Tensor:
         return self._get("f:" + name, [name], lambda p: p.float().contiguous())
 
 
 class StatsArena:
-    """fp64 (sum, sumsq) accumulators for every InstanceNorm of one forward, zeroed with a single memset."""
+    """fp64 accumulators (InstanceNorm statistics of one forward / reduction sums of one backward), zeroed with a
+    single memset."""
 
     def __init__(self, device, capacity: int = 1 << 18):
         self.buf = torch.zeros(capacity, dtype=torch.float64, device=device)
@@ -129,13 +202,51 @@ class StatsArena:
         self.buf.zero_()
         self.off = 0
 
-    def take(self, B: int, C: int) -> torch.Tensor:
-        n = B * C * 2
+    def take(self, B: int, C: int, width: int = 2) -> torch.Tensor:
+        n = B * C * width
         if self.off + n > self.buf.numel():
             raise RuntimeError("InstanceNorm statistics arena exhausted")
-        t = self.buf[self.off:self.off + n].view(B, C, 2)
+        t = self.buf[self.off:self.off + n].view(B, C, width)
         self.off += n
         return t
+
+
+class GradArena:
+    """fp32 accumulators for every parameter gradient of one backward pass (the tensor-core wgrad kernel and the
+    column-sum kernel accumulate with reductions), zeroed with a single memset."""
+
+    def __init__(self, device, capacity: int):
+        self.buf = torch.zeros(capacity, dtype=F32, device=device)
+        self.off = 0
+
+    def reset(self):
+        self.buf.zero_()
+        self.off = 0
+
+    def take(self, *shape) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        n_al = -(-n // 64) * 64
+        if self.off + n_al > self.buf.numel():
+            raise RuntimeError("parameter-gradient arena exhausted")
+        t = self.buf[self.off:self.off + n].view(*shape)
+        self.off += n_al
+        return t
+
+
+def _key(t: torch.Tensor):
+    return (t.data_ptr(), int(t.shape[-1]), int(t.stride(-2)) if t.dim() >= 2 else 0, t.numel())
+
+
+class Tape:
+    """Closures of one training forward, gradients of its activations, and the parameter-gradient records."""
+
+    def __init__(self):
+        self.fns: List[Callable[[], None]] = []
+        self.grads: Dict[tuple, torch.Tensor] = {}
+        self.alias: Dict[tuple, Tuple[torch.Tensor, int]] = {}
+        self.wrecs: List[tuple] = []  # (kind, name, buffer, meta)
 
 
 class Engine:
@@ -143,6 +254,9 @@ class Engine:
         self.w = WeightCache(params)
         self.dev = device
         self.stats = StatsArena(device)
+        self.tape: Optional[Tape] = None
+        self.bsums: Optional[StatsArena] = None
+        self.garena: Optional[GradArena] = None
 
     # ------------------------------------------------------------------ helpers
     def _empty(self, *shape, dtype=BF16):
@@ -158,82 +272,436 @@ class Engine:
         B, X, Y, Z, _ = x.shape
         return (X * Y * Z, 1, 1, B)
 
-    def conv3x3(self, x, pw: PackedWeight, stats=None, out=None):
+    # ------------------------------------------------------------------ tape plumbing (training only)
+    def begin_training_forward(self):
+        self.tape = Tape()
+        self.stats = StatsArena(self.dev, 1 << 20)  # owned by this tape: the backward reads the forward's statistics
+        if self.bsums is None:
+            self.bsums = StatsArena(self.dev, 1 << 21)
+        if self.garena is None:
+            n = sum(p.numel() for p in self.w.params.values())
+            self.garena = GradArena(self.dev, int(n * 1.15) + (32 << 20))
+
+    def _alias(self, view: torch.Tensor, base: torch.Tensor, c0: int):
+        if self.tape is not None:
+            self.tape.alias[_key(view)] = (base, c0)
+
+    def _g(self, t: torch.Tensor) -> Optional[torch.Tensor]:
+        """Gradient that has arrived for activation `t` (None if no consumer produced one)."""
+        k = _key(t)
+        al = self.tape.alias.get(k)
+        if al is not None:
+            base, c0 = al
+            bg = self.tape.grads.get(_key(base))
+            return None if bg is None else bg.view(base.shape)[..., c0:c0 + t.shape[-1]]
+        g = self.tape.grads.get(k)
+        if g is not None and g.shape != t.shape and g.is_contiguous():
+            g = g.view(t.shape)
+        return g
+
+    def _g16(self, t: torch.Tensor) -> Optional[torch.Tensor]:
+        g = self._g(t)
+        if g is not None and g.dtype != BF16:
+            g16 = self._empty(*g.shape)
+            ops.cast_f32_bf16(g, g16)
+            return g16
+        return g
+
+    def _acc(self, t: torch.Tensor, g: torch.Tensor):
+        """Add gradient `g` (freshly computed, ownership passes to the tape) to activation `t`."""
+        k = _key(t)
+        al = self.tape.alias.get(k)
+        if al is not None:
+            base, c0 = al
+            bk = _key(base)
+            bg = self.tape.grads.get(bk)
+            if bg is None:
+                bg = torch.zeros(base.shape, dtype=base.dtype, device=self.dev)
+                self.tape.grads[bk] = bg
+            ops.accumulate(g, bg.view(base.shape)[..., c0:c0 + t.shape[-1]])
+            return
+        cur = self.tape.grads.get(k)
+        if cur is None:
+            if g.dtype != t.dtype or not g.is_contiguous():
+                buf = torch.zeros(t.shape, dtype=t.dtype, device=self.dev)
+                ops.accumulate(g, buf)
+                g = buf
+            self.tape.grads[k] = g
+        else:
+            ops.accumulate(g, cur)
+
+    def _done(self, t: torch.Tensor):
+        if _key(t) not in self.tape.alias:
+            self.tape.grads.pop(_key(t), None)
+
+    def _rec(self, fn):
+        if self.tape is not None:
+            self.tape.fns.append(fn)
+
+    def backward(self, out_grads: List[Tuple[torch.Tensor, Optional[torch.Tensor]]], want=()):
+        """out_grads: (forward output tensor, its gradient or None).  Returns ({parameter name: fp32 gradient},
+        [gradient of each activation in `want`])."""
+        tape = self.tape
+        if tape is None:
+            raise RuntimeError("backward() without a recorded training forward")
+        self.bsums.reset()
+        self.garena.reset()
+        for t, g in out_grads:
+            if g is not None:
+                tape.grads[_key(t)] = g.contiguous()
+        for fn in reversed(tape.fns):
+            fn()
+        igrads = [None if a is None else self._g(a) for a in want]
+        grads = self._finalize_param_grads(tape)
+        self.tape = None
+        return grads, igrads
+
+    def _finalize_param_grads(self, tape: Tape) -> Dict[str, torch.Tensor]:
+        out: Dict[str, torch.Tensor] = {}
+
+        def put(name, g):
+            name = name.lstrip(".")
+            p = self.w.params[name]
+            g = g.reshape(p.shape)
+            out[name] = g if name not in out else out[name] + g
+
+        for kind, name, buf, meta in tape.wrecs:
+            if kind == "lin":        # buf [K, Npad] -> [N, K]
+                n, k = self.w.params[(name + ".weight").lstrip(".")].shape
+                put(name + ".weight", buf[:k, :n].t())
+            elif kind == "conv1":    # buf [cip, cop] -> [co, ci, 1, 1, 1]
+                co, ci = self.w.params[(name + ".weight").lstrip(".")].shape[:2]
+                put(name + ".weight", buf[:ci, :co].t())
+            elif kind == "conv3":    # buf [27*cip, cop] -> [co, ci, 3, 3, 3]
+                co, ci = self.w.params[(name + ".weight").lstrip(".")].shape[:2]
+                cip = buf.shape[0] // 27
+                put(name + ".weight", buf.view(3, 3, 3, cip, -1)[..., :ci, :co].permute(4, 3, 0, 1, 2))
+            elif kind == "convt":    # buf [ci, k3*co] -> [ci, co, kx, ky, kz]
+                ci, co, kx, ky, kz = self.w.params[(name + ".weight").lstrip(".")].shape
+                put(name + ".weight", buf.view(ci, kx, ky, kz, co).permute(0, 4, 1, 2, 3))
+            elif kind == "ps":       # buf [corg*k3, k3*co]: the k3 diagonal blocks hold the Linear's gradient
+                co, corg = self.w.params[(name + ".weight").lstrip(".")].shape
+                k3 = buf.shape[0] // corg
+                put(name + ".weight", torch.einsum("csso->oc", buf.view(corg, k3, k3, co)))
+            elif kind == "ps_bias":  # buf [k3*co]
+                co = self.w.params[(name + ".bias").lstrip(".")].shape[0]
+                put(name + ".bias", buf.view(-1, co).sum(0))
+            elif kind == "cin1":     # buf [kpad, 64] -> [co, 1, kx, ky, kz]
+                p = self.w.params[(name + ".weight").lstrip(".")]
+                taps = p[0].numel()
+                put(name + ".weight", buf[:taps, :p.shape[0]].t())
+            elif kind == "vec":      # bias / LayerNorm vectors (possibly padded)
+                p = self.w.params[name.lstrip(".")]
+                put(name, buf.reshape(-1)[:p.numel()])
+            elif kind == "relbias":  # buf [heads, key, query] -> embedding [(2w-1)^3, heads]
+                p = self.w.params[(name + ".weight").lstrip(".")]
+                idx = rel_pos_index(meta).to(self.dev).reshape(-1)
+                g = torch.zeros(p.shape, dtype=F32, device=self.dev)
+                g.index_add_(0, idx, buf.permute(2, 1, 0).reshape(-1, p.shape[1]))
+                put(name + ".weight", g)
+            else:  # pragma: no cover
+                raise KeyError(kind)
+        return out
+
+    # ------------------------------------------------------------------ primitives (forward + recorded backward)
+    def gemm(self, a, kind: str, name: str, out, *, dims, extra=None, stats=None, act=ACT_NONE, residual=None,
+             out_mode=OUT_BF16, a_c=None, a_needs_grad: bool = True):
+        """Tensor-core contraction through ctu_umma_gemm with the packed weight (kind, name)."""
+        pw = self.w.get(kind, name, extra)
+        ac = int(a_c if a_c is not None else pw.a_c)
+        ops.gemm(a, pw, out, dims=dims, stats=stats, act=act, residual=residual, out_mode=out_mode, a_c=ac)
+        if self.tape is None:
+            return out
+        assert act == ACT_NONE, "training keeps the pre-activation: use gelu()"
+
+        def bw():
+            g = self._g(out)
+            if g is None:
+                return
+            if residual is not None:
+                self._acc(residual, g)  # identity branch (g stays valid: nothing accumulates into it before we return)
+            if out_mode == OUT_F32_CF:   # logits head: NCDHW fp32 -> channels-last bf16, zero-padded to 64 channels
+                B, _, X, Y, Z = out.shape
+                g16 = self._empty(B, X, Y, Z, 64)
+                ops.cf_to_cl(g.contiguous(), g16, 64)
+                n_eff = 64
+            elif pw.convt is not None:   # up-sampling GEMM: gather the sub-voxels back into GEMM columns
+                co, u1, u2, u3 = pw.convt
+                B, Xo, Yo, Zo, _ = out.shape
+                gv = g if g.dtype == BF16 else self._g16(out)
+                g16 = self._empty(B, Xo // u3, Yo // u2, Zo // u1, u1 * u2 * u3 * co)
+                ops.space_to_depth(gv, g16, (u3, u2, u1))
+                n_eff = pw.n_real
+            else:
+                g16 = g if g.dtype == BF16 else self._g16(out)
+                n_eff = pw.n_real
+            ksize = pw.ksize
+            # parameter gradients
+            dw = self.garena.take(ksize ** 3 * ac, n_eff)
+            ops.wgrad(a, g16, dw, dims=dims, ksize=ksize, x_c=ac, n=n_eff)
+            self.tape.wrecs.append((kind, name, dw, None))
+            if pw.bias is not None:
+                db = self.garena.take(n_eff)
+                ops.colsum(g16.reshape(-1, g16.shape[-1]) if g16.is_contiguous() else g16, db, n=n_eff)
+                self.tape.wrecs.append(("ps_bias" if kind == "ps" else "vec", name if kind == "ps" else name + ".bias", db, None))
+            # input gradient
+            if a_needs_grad:
+                pt = self.w.get_t(kind, name, extra)
+                da = self._empty(*a.shape[:-1], ac)
+                ops.gemm(g16, pt, da, dims=dims, a_c=n_eff)
+                self._acc(a, da)
+            self._done(out)
+        self._rec(bw)
+        return out
+
+    def in_apply(self, x, st, *, res=None, rstats=None, out=None):
+        """out = lrelu(IN(x) [+ res | + IN(res)]) (resnet.py:110-124; hybrid_CTUNet.py:95-104)."""
+        if out is None:
+            out = self._empty(*x.shape)
+        ops.in_apply(x, st, out, res=res, rstats=rstats, act=True)
+        if self.tape is not None:
+            def bw():
+                g = self._g(out)
+                if g is None:
+                    return
+                B, C = x.shape[0], x.shape[-1]
+                dx = self._empty(*x.shape)
+                dres = self._empty(*res.shape) if res is not None else None
+                ops.in_backward(g, out, x, st, dx, res=res, rstats=rstats, dres=dres, sums=self.bsums.take(B, C, 4))
+                self._acc(x, dx)
+                if res is not None:
+                    self._acc(res, dres)
+                self._done(out)
+            self._rec(bw)
+        return out
+
+    def layernorm(self, x, name: str, out, *, add_name: Optional[str] = None):
+        gamma, beta = self.w.f32(name + ".weight"), self.w.f32(name + ".bias")
+        add = self.w.f32(add_name) if add_name else None
+        ops.layernorm(x, gamma, beta, out, add=add)
+        if self.tape is not None:
+            def bw():
+                dy = self._g(out)
+                if dy is None:
+                    return
+                C = x.shape[-1]
+                if add is not None:  # pos_embedding: sum of the output gradient over the batch
+                    dadd = self.garena.take(add.numel())
+                    rows = x.numel() // add.numel()
+                    dyf = dy if dy.is_contiguous() else dy.contiguous()
+                    ops.colsum(dyf.view(rows, add.numel()), dadd)
+                    self.tape.wrecs.append(("vec", add_name, dadd, None))
+                dy16 = dy if dy.dtype == BF16 else self._g16(out)
+                dg, db = self.garena.take(C), self.garena.take(C)
+                gx = self._g(x)
+                x2 = x.reshape(-1, C) if x.is_contiguous() else x
+                if gx is None:
+                    dx = torch.empty(x.shape, dtype=x.dtype, device=self.dev)
+                    ops.layernorm_backward(x2, gamma, dy16.reshape(-1, C) if dy16.is_contiguous() else dy16, dg, db,
+                                           dx_f32=dx.view(-1, C) if dx.dtype == F32 else None,
+                                           dx_bf16=dx.view(-1, C) if dx.dtype == BF16 else None)
+                    self._acc(x, dx)
+                else:  # join the gradient already flowing along the residual stream, in place
+                    gx2 = gx.reshape(-1, C) if gx.is_contiguous() else gx
+                    ops.layernorm_backward(x2, gamma, dy16.reshape(-1, C) if dy16.is_contiguous() else dy16, dg, db,
+                                           dx_in=gx2, dx_f32=gx2 if gx.dtype == F32 else None,
+                                           dx_bf16=gx2 if gx.dtype == BF16 else None)
+                self.tape.wrecs.append(("vec", name + ".weight", dg, None))
+                self.tape.wrecs.append(("vec", name + ".bias", db, None))
+                self._done(out)
+            self._rec(bw)
+        return out
+
+    def gelu(self, x):
+        y = self._empty(*x.shape)
+        ops.gelu(x, y)
+
+        def bw():
+            g = self._g(y)
+            if g is None:
+                return
+            dx = self._empty(*x.shape)
+            ops.gelu_backward(x, g, dx)
+            self._acc(x, dx)
+            self._done(y)
+        self._rec(bw)
+        return y
+
+    def attention(self, qkv, out, *, dim_head, n, windows=0, mode=0, bias_name=None, grid=(1, 1, 1, 1)):
+        bias = self.w.rel_bias(bias_name) if bias_name else None
+        if self.tape is None:
+            ops.attention(qkv, out, dim_head=dim_head, n=n, windows=windows, mode=mode, bias=bias, grid=grid, w=6)
+            return out
+        C = out.shape[-1]
+        heads = C // dim_head
+        lse = self._empty(qkv.shape[0], heads, dtype=F32)
+        ops.attention(qkv, out, dim_head=dim_head, n=n, windows=windows, mode=mode, bias=bias, grid=grid, w=6, lse=lse)
+
+        def bw():
+            g = self._g(out)
+            if g is None:
+                return
+            rows = qkv.shape[0]
+            dqkv = self._empty(rows, 3 * C)
+            dq = torch.zeros(rows, C, dtype=F32, device=self.dev)
+            nwin = windows if mode == 0 else rows // n
+            ds = bias_t = None
+            if bias_name:
+                bias_t = self.w.rel_bias_t(bias_name)
+                ds = self._empty(nwin, heads, n, n)
+            ops.attention_backward(qkv, out, g, lse, dqkv, dq, dim_head=dim_head, n=n, windows=windows, mode=mode,
+                                   bias_t=bias_t, ds_out=ds, grid=grid, w=6)
+            ops.cast_f32_bf16(dq, dqkv[:, :C])
+            if bias_name:
+                dbt = self.garena.take(heads, n, n)
+                ops.colsum(ds.view(nwin, heads * n * n), dbt.view(-1))
+                self.tape.wrecs.append(("relbias", bias_name, dbt, 6))
+            self._acc(qkv, dqkv)
+            self._done(out)
+        self._rec(bw)
+        return out
+
+    def pwa_fuse(self, q1, q2, out):
+        ops.pwa_fuse(q1, q2, out)
+        if self.tape is not None:
+            def bw():
+                g = self._g(out)
+                if g is None:
+                    return
+                d1, d2 = self._empty(*q1.shape), self._empty(*q2.shape)
+                ops.pwa_fuse_backward(q1, q2, g, d1, d2)
+                self._acc(q1, d1)
+                self._acc(q2, d2)
+                self._done(out)
+            self._rec(bw)
+        return out
+
+    def subsample(self, x, out, stride):
+        ops.subsample(x, out, stride)
+        if self.tape is not None:
+            def bw():
+                g = self._g(out)
+                if g is None:
+                    return
+                gx = self._g(x)
+                if gx is None:
+                    dx = self._empty(*x.shape)
+                    ops.subsample_backward(g, dx, stride)
+                    self._acc(x, dx)
+                else:
+                    ops.subsample_backward(g, gx, stride, accumulate=True)
+                self._done(out)
+            self._rec(bw)
+        return out
+
+    def conv_cin1(self, x_in, name: str, out, *, k, s, p):
+        ops.conv_cin1(x_in, self.w.conv_cin1(name), out, k=k, s=s, p=p)
+        if self.tape is not None:
+            def bw():
+                g = self._g(out)
+                if g is None:
+                    return
+                taps = k[0] * k[1] * k[2]
+                kpad = -(-taps // 64) * 64
+                B, Xo, Yo, Zo, _ = out.shape
+                col = self._empty(B, Xo, Yo, Zo, kpad)
+                ops.im2col_cin1(x_in, col, k=k, s=s, p=p)
+                dw = self.garena.take(kpad, 64)
+                ops.wgrad(col, g, dw, dims=(Zo, Yo, Xo, B), x_c=kpad, n=64)
+                self.tape.wrecs.append(("cin1", name, dw, None))
+                self._done(out)
+            self._rec(bw)
+        return out
+
+    def patchify_ln(self, x_in, pf: int, name: str, tok):
+        gamma, beta = self.w.f32(name + ".weight"), self.w.f32(name + ".bias")
+        ops.patchify_ln(x_in, pf, gamma, beta, tok)
+        if self.tape is not None:
+            def bw():
+                g = self._g16(tok)
+                if g is None:
+                    return
+                dg, db = self.garena.take(gamma.numel()), self.garena.take(gamma.numel())
+                ops.patchify_ln_backward(x_in, pf, g, dg, db)
+                self.tape.wrecs.append(("vec", name + ".weight", dg, None))
+                self.tape.wrecs.append(("vec", name + ".bias", db, None))
+                self._done(tok)
+            self._rec(bw)
+        return tok
+
+    # ------------------------------------------------------------------ contractions by role
+    def conv3x3(self, x, name: str, stats=None, out=None):
+        pw = self.w.conv3(name)
         B, X, Y, Z, _ = x.shape
         if out is None:
             out = self._empty(B, X, Y, Z, pw.n_real)
-        ops.gemm(x, pw, out, dims=self._dims(x), stats=stats, a_c=pw.a_c)
-        return out
+        return self.gemm(x, "conv3", name, out, dims=self._dims(x), stats=stats)
 
-    def conv1x1(self, x, pw: PackedWeight, stats=None, out=None):
+    def conv1x1(self, x, name: str, stats=None, out=None):
+        pw = self.w.conv1(name)
         B, X, Y, Z, _ = x.shape
         if out is None:
             out = self._empty(B, X, Y, Z, pw.n_real)
-        ops.gemm(x, pw, out, dims=self._flat_dims(x), stats=stats, a_c=pw.a_c)
-        return out
+        return self.gemm(x, "conv1", name, out, dims=self._flat_dims(x), stats=stats)
 
-    def up_gemm(self, x, pw: PackedWeight, out=None, a_c=None):
+    def up_gemm(self, x, kind: str, name: str, extra=None, out=None):
         """ConvTranspose3d(k=s) / pixel-shuffle+Linear: [B,X,Y,Z,Cin] -> [B,X*ux,Y*uy,Z*uz,Cout]."""
+        pw = self.w.get(kind, name, extra)
         B, X, Y, Z, _ = x.shape
         co, uz, uy, ux = pw.convt
         if out is None:
             out = self._empty(B, X * ux, Y * uy, Z * uz, co)
-        ops.gemm(x, pw, out, dims=self._dims(x), a_c=a_c)
-        return out
+        return self.gemm(x, kind, name, out, dims=self._dims(x), extra=extra)
 
-    def head(self, x, pw: PackedWeight, a_c=None):
+    def head(self, x, kind: str, name: str, a_c=None):
         """UnetOutBlock / DecoderLinear: per-voxel C -> n_cls with bias, fp32 NCDHW output."""
+        pw = self.w.get(kind, name, True)
         B, X, Y, Z, _ = x.shape
-        out = self._empty(B, pw.n_real, X, Y, Z, dtype=torch.float32)
-        ops.gemm(x, pw, out, dims=self._flat_dims(x), out_mode=OUT_F32_CF, a_c=a_c)
-        return out
+        out = self._empty(B, pw.n_real, X, Y, Z, dtype=F32)
+        return self.gemm(x, kind, name, out, dims=self._flat_dims(x), extra=True, out_mode=OUT_F32_CF, a_c=a_c)
 
     # ------------------------------------------------------------------ networks/resnet.py
     def bottleneck(self, pre: str, x, stride, has_down: bool):
         """resnet.py:106-126: 1x1 -> IN -> lrelu -> 3x3x3(stride) -> IN -> lrelu -> 1x1 -> IN (+res) -> lrelu."""
         B = x.shape[0]
-        w1, w2, w3 = self.w.conv1(pre + ".conv1.conv"), self.w.conv3(pre + ".conv2.conv"), self.w.conv1(pre + ".conv3.conv")
-        st1 = self.stats.take(B, w1.n_real)
-        c1 = self.conv1x1(x, w1, st1)
-        ops.in_apply(c1, st1, c1, act=True)
-        st2 = self.stats.take(B, w2.n_real)
+        n1, n2, n3 = pre + ".conv1.conv", pre + ".conv2.conv", pre + ".conv3.conv"
+        st1 = self.stats.take(B, self.w.conv1(n1).n_real)
+        a1 = self.in_apply(self.conv1x1(x, n1, st1), st1)
+        st2 = self.stats.take(B, self.w.conv3(n2).n_real)
         strided = tuple(stride) != (1, 1, 1)
         if not strided:
-            c2 = self.conv3x3(c1, w2, st2)
+            c2 = self.conv3x3(a1, n2, st2)
         else:
             # stride-s 3x3x3, pad 1 == the stride-1 result sampled at multiples of s
-            full = self.conv3x3(c1, w2)
+            full = self.conv3x3(a1, n2)
             _, X, Y, Z, C = full.shape
             c2 = self._empty(B, -(-X // stride[0]), -(-Y // stride[1]), -(-Z // stride[2]), C)
-            ops.subsample(full, c2, stride)
+            self.subsample(full, c2, stride)
             ops.in_stats(c2, st2)
-        ops.in_apply(c2, st2, c2, act=True)
-        st3 = self.stats.take(B, w3.n_real)
-        c3 = self.conv1x1(c2, w3, st3)
+        a2 = self.in_apply(c2, st2)
+        st3 = self.stats.take(B, self.w.conv1(n3).n_real)
+        c3 = self.conv1x1(a2, n3, st3)
         if has_down:
-            wd = self.w.conv1(pre + ".downsample.0.conv")
+            nd = pre + ".downsample.0.conv"
             xs = x
             if strided:
                 _, X, Y, Z, C = x.shape
                 xs = self._empty(B, -(-X // stride[0]), -(-Y // stride[1]), -(-Z // stride[2]), C)
-                ops.subsample(x, xs, stride)
-            std = self.stats.take(B, wd.n_real)
-            r = self.conv1x1(xs, wd, std)
-            ops.in_apply(c3, st3, c3, res=r, rstats=std, act=True)
-        else:
-            ops.in_apply(c3, st3, c3, res=x, act=True)
-        return c3
+                self.subsample(x, xs, stride)
+            std = self.stats.take(B, self.w.conv1(nd).n_real)
+            r = self.conv1x1(xs, nd, std)
+            return self.in_apply(c3, st3, res=r, rstats=std)
+        return self.in_apply(c3, st3, res=x)
 
     def resnet(self, pre: str, x_in, layers: List[int]):
         """resnet.py:213-230 (no max pool): stem k7 s(2,2,1) -> IN -> lrelu -> 4 stages; returns 4 feature maps."""
         B, _, X, Y, Z = x_in.shape
         s0 = DS_STRIDE[0]
-        wst = self.w.conv_cin1(pre + "conv1.conv")
         x = self._empty(B, (X + 6 - 7) // s0[0] + 1, (Y + 6 - 7) // s0[1] + 1, (Z + 6 - 7) // s0[2] + 1, 64)
-        ops.conv_cin1(x_in, wst, x, k=(7, 7, 7), s=s0, p=(3, 3, 3))
+        self.conv_cin1(x_in, pre + "conv1.conv", x, k=(7, 7, 7), s=s0, p=(3, 3, 3))
         st = self.stats.take(B, 64)
         ops.in_stats(x, st)
-        ops.in_apply(x, st, x, act=True)
+        x = self.in_apply(x, st)
         feats = []
         strides = [(1, 1, 1), DS_STRIDE[1], DS_STRIDE[2], DS_STRIDE[3]]
         for li, nb in enumerate(layers):
@@ -243,125 +711,103 @@ class Engine:
         return feats
 
     # ------------------------------------------------------------------ networks/vit.py
-    def ffn(self, pre: str, x, out=None):
-        """LN -> Linear -> GELU -> Linear, + x (vit.py:34-44,95; hybrid_CTUNet.py:517-526 inside Residual)."""
+    def ffn(self, pre: str, x, out_dtype=None):
+        """LN -> Linear -> GELU -> Linear, + x (vit.py:34-44,95; hybrid_CTUNet.py:517-526 inside Residual).
+        Returns a new tensor (the residual stream is never updated in place)."""
         M, D = x.shape
-        h = self._empty(M, D)
-        ops.layernorm(x, self.w.f32(pre + ".net.0.weight"), self.w.f32(pre + ".net.0.bias"), h)
-        w1, w2 = self.w.linear(pre + ".net.1"), self.w.linear(pre + ".net.4")
-        f = self._empty(M, w1.n_real)
-        ops.gemm(h, w1, f, dims=(M, 1, 1, 1), act=ACT_GELU)
-        out = x if out is None else out
-        ops.gemm(f, w2, out, dims=(M, 1, 1, 1), out_mode=OUT_F32 if out.dtype == torch.float32 else OUT_BF16, residual=x)
-        return out
+        h = self.layernorm(x, pre + ".net.0", self._empty(M, D))
+        n1, n2 = pre + ".net.1", pre + ".net.4"
+        hidden = self.w.linear(n1).n_real
+        if self.tape is None:
+            f = self.gemm(h, "lin", n1, self._empty(M, hidden), dims=(M, 1, 1, 1), extra=True, act=ACT_GELU)
+        else:
+            f = self.gelu(self.gemm(h, "lin", n1, self._empty(M, hidden), dims=(M, 1, 1, 1), extra=True))
+        out = self._empty(M, D, dtype=out_dtype or x.dtype)
+        return self.gemm(f, "lin", n2, out, dims=(M, 1, 1, 1), extra=True, residual=x,
+                         out_mode=OUT_F32 if out.dtype == F32 else OUT_BF16)
 
     def vit_attention(self, pre: str, x, B: int, n: int, heads: int):
-        """vit.py:66-78 + residual (vit.py:94); x: fp32 [B*n, D] updated in place."""
+        """vit.py:66-78 + residual (vit.py:94); x: fp32 [B*n, D]; returns the updated stream."""
         M, D = x.shape
-        h = self._empty(M, D)
-        ops.layernorm(x, self.w.f32(pre + ".norm.weight"), self.w.f32(pre + ".norm.bias"), h)
-        wq, wo = self.w.linear(pre + ".to_qkv", bias=False), self.w.linear(pre + ".to_out.0")
-        qkv = self._empty(M, 3 * D)
-        ops.gemm(h, wq, qkv, dims=(M, 1, 1, 1))
-        a = self._empty(M, D)
-        ops.attention(qkv, a, dim_head=D // heads, n=n, windows=B, mode=0)
-        ops.gemm(a, wo, x, dims=(M, 1, 1, 1), out_mode=OUT_F32, residual=x)
-        return x
+        h = self.layernorm(x, pre + ".norm", self._empty(M, D))
+        qkv = self.gemm(h, "lin", pre + ".to_qkv", self._empty(M, 3 * D), dims=(M, 1, 1, 1), extra=False)
+        a = self.attention(qkv, self._empty(M, D), dim_head=D // heads, n=n, windows=B, mode=0)
+        return self.gemm(a, "lin", pre + ".to_out.0", self._empty(M, D, dtype=F32), dims=(M, 1, 1, 1), extra=True,
+                         out_mode=OUT_F32, residual=x)
 
     def vit(self, pre: str, x_in, pf: int, depth: int, heads: int):
         """vit.py:130-139: returns the fp32 token stream [B*n, dim]."""
         B, _, X, Y, Z = x_in.shape
         n = (X // 16) * (Y // 16) * (Z // pf)
         e = pre + "to_patch_embedding"
-        tok = self._empty(B * n, 256 * pf)
-        ops.patchify_ln(x_in, pf, self.w.f32(e + ".1.weight"), self.w.f32(e + ".1.bias"), tok)
-        wemb = self.w.linear(e + ".2")
-        dim = wemb.n_real
-        emb = self._empty(B * n, dim, dtype=torch.float32)
-        ops.gemm(tok, wemb, emb, dims=(B * n, 1, 1, 1), out_mode=OUT_F32)
-        x = self._empty(B * n, dim, dtype=torch.float32)
-        ops.layernorm(emb, self.w.f32(e + ".3.weight"), self.w.f32(e + ".3.bias"), x, add=self.w.f32(pre + "pos_embedding"))
+        tok = self.patchify_ln(x_in, pf, e + ".1", self._empty(B * n, 256 * pf))
+        dim = self.w.linear(e + ".2").n_real
+        emb = self.gemm(tok, "lin", e + ".2", self._empty(B * n, dim, dtype=F32), dims=(B * n, 1, 1, 1), extra=True,
+                        out_mode=OUT_F32, a_needs_grad=True)
+        x = self.layernorm(emb, e + ".3", self._empty(B * n, dim, dtype=F32), add_name=pre + "pos_embedding")
         for i in range(depth):
             t = f"{pre}transformer.{i}"
-            self.vit_attention(t + ".attn", x, B, n, heads)
-            self.ffn(t + ".ff", x)
+            x = self.vit_attention(t + ".attn", x, B, n, heads)
+            x = self.ffn(t + ".ff", x)
         return x, n
 
     # ------------------------------------------------------------------ networks/hybrid_CTUNet.py
     def res_block(self, pre: str, x, cin: int, cout: int, out=None):
         """hybrid_CTUNet.py:93-105 (k3, stride 1): conv-IN-lrelu-conv-IN, + (conv1x1-IN)(x) or x, lrelu."""
         B = x.shape[0]
-        w1, w2 = self.w.conv3(pre + ".conv1.conv"), self.w.conv3(pre + ".conv2.conv")
-        st1 = self.stats.take(B, w1.n_real)
-        c1 = self.conv3x3(x, w1, st1)
-        ops.in_apply(c1, st1, c1, act=True)
-        st2 = self.stats.take(B, w2.n_real)
-        c2 = self.conv3x3(c1, w2, st2)
-        out = c2 if out is None else out
+        n1, n2 = pre + ".conv1.conv", pre + ".conv2.conv"
+        st1 = self.stats.take(B, self.w.conv3(n1).n_real)
+        a1 = self.in_apply(self.conv3x3(x, n1, st1), st1)
+        st2 = self.stats.take(B, self.w.conv3(n2).n_real)
+        c2 = self.conv3x3(a1, n2, st2)
         if cin != cout:
-            w3 = self.w.conv1(pre + ".conv3.conv")
-            st3 = self.stats.take(B, w3.n_real)
-            r = self.conv1x1(x, w3, st3)
-            ops.in_apply(c2, st2, out, res=r, rstats=st3, act=True)
-        else:
-            ops.in_apply(c2, st2, out, res=x, act=True)
-        return out
+            n3 = pre + ".conv3.conv"
+            st3 = self.stats.take(B, self.w.conv1(n3).n_real)
+            r = self.conv1x1(x, n3, st3)
+            return self.in_apply(c2, st2, res=r, rstats=st3, out=out)
+        return self.in_apply(c2, st2, res=x, out=out)
 
     def res_block_cin1(self, pre: str, x_in, out=None):
         """ResBlock(1 -> 64) of vit_encoder0 (hybrid_CTUNet.py:786-793): conv1/conv3 have one input channel."""
         B, _, X, Y, Z = x_in.shape
-        c1 = self._empty(B, X, Y, Z, 64)
-        ops.conv_cin1(x_in, self.w.conv_cin1(pre + ".conv1.conv"), c1, k=(3, 3, 3), s=(1, 1, 1), p=(1, 1, 1))
+        c1 = self.conv_cin1(x_in, pre + ".conv1.conv", self._empty(B, X, Y, Z, 64), k=(3, 3, 3), s=(1, 1, 1), p=(1, 1, 1))
         st1 = self.stats.take(B, 64)
         ops.in_stats(c1, st1)
-        ops.in_apply(c1, st1, c1, act=True)
-        w2 = self.w.conv3(pre + ".conv2.conv")
+        a1 = self.in_apply(c1, st1)
         st2 = self.stats.take(B, 64)
-        c2 = self.conv3x3(c1, w2, st2)
-        ops.conv_cin1(x_in, self.w.conv_cin1(pre + ".conv3.conv"), c1, k=(1, 1, 1), s=(1, 1, 1), p=(0, 0, 0))
+        c2 = self.conv3x3(a1, pre + ".conv2.conv", st2)
+        r = self.conv_cin1(x_in, pre + ".conv3.conv", self._empty(B, X, Y, Z, 64), k=(1, 1, 1), s=(1, 1, 1), p=(0, 0, 0))
         st3 = self.stats.take(B, 64)
-        ops.in_stats(c1, st3)
-        out = c2 if out is None else out
-        ops.in_apply(c2, st2, out, res=c1, rstats=st3, act=True)
-        return out
+        ops.in_stats(r, st3)
+        return self.in_apply(c2, st2, res=r, rstats=st3, out=out)
 
     def pixelweight_attention(self, pre: str, x1, x2):
         """hybrid_CTUNet.py:645-669, the binary cross-weight fusion of two [B,X,Y,Z,C] maps."""
         B, X, Y, Z, C = x1.shape
         T = B * X * Y * Z
-        h = self._empty(T, C)
         q = []
         for x, nrm, lin in ((x1, ".norm1", ".to_qkv1"), (x2, ".norm2", ".to_qkv2")):
-            ops.layernorm(x.reshape(T, C), self.w.f32(pre + nrm + ".weight"), self.w.f32(pre + nrm + ".bias"), h)
-            qkv = self._empty(T, 3 * C)
-            ops.gemm(h, self.w.linear(pre + lin, bias=False), qkv, dims=(T, 1, 1, 1))
-            q.append(qkv)
-        ops.pwa_fuse(q[0], q[1], h)
-        out = self._empty(B, X, Y, Z, C)
-        ops.gemm(h, self.w.linear(pre + ".to_out.0", bias=False), out, dims=(T, 1, 1, 1))
-        return out
+            h = self.layernorm(x.reshape(T, C), pre + nrm, self._empty(T, C))
+            q.append(self.gemm(h, "lin", pre + lin, self._empty(T, 3 * C), dims=(T, 1, 1, 1), extra=False))
+        f = self.pwa_fuse(q[0], q[1], self._empty(T, C))
+        return self.gemm(f, "lin", pre + ".to_out.0", self._empty(B, X, Y, Z, C), dims=(T, 1, 1, 1), extra=False)
 
     def up_2fusion(self, pre: str, inp, skip_conv, skip_vit, cout: int):
         """hybrid_CTUNet.py:329-341."""
         skip = self.pixelweight_attention(pre + ".pixelweight_attention1", skip_conv, skip_vit)
         skip = self.res_block(pre + ".up_addconv_block1", skip, cout, cout)
-        up = self.up_gemm(inp, self.w.convt(pre + ".transp_conv.conv"))
+        up = self.up_gemm(inp, "convt", pre + ".transp_conv.conv")
         fused = self.pixelweight_attention(pre + ".pixelweight_attention2", up, skip)
         return self.res_block(pre + ".up_addconv_block2", fused, cout, cout)
 
-    def window_attention(self, pre: str, x, grid, mode: int, out=None):
-        """Residual(MultiAxisAttention) (hybrid_CTUNet.py:481-511); x: [T, D] residual stream, updated in place
-        unless `out` is given."""
+    def window_attention(self, pre: str, x, grid, mode: int):
+        """Residual(MultiAxisAttention) (hybrid_CTUNet.py:481-511); x: [T, D] residual stream; returns the new stream."""
         T, D = x.shape
-        out = x if out is None else out
-        h = self._empty(T, D)
-        ops.layernorm(x, self.w.f32(pre + ".norm.weight"), self.w.f32(pre + ".norm.bias"), h)
-        qkv = self._empty(T, 3 * D)
-        ops.gemm(h, self.w.linear(pre + ".to_qkv", bias=False), qkv, dims=(T, 1, 1, 1))
-        ops.attention(qkv, h, dim_head=32, n=216, mode=mode, bias=self.w.rel_bias(pre + ".rel_pos_bias"), grid=grid, w=6)
-        ops.gemm(h, self.w.linear(pre + ".to_out.0", bias=False), out, dims=(T, 1, 1, 1),
-                 out_mode=OUT_F32 if out.dtype == torch.float32 else OUT_BF16, residual=x)
-        return out
+        h = self.layernorm(x, pre + ".norm", self._empty(T, D))
+        qkv = self.gemm(h, "lin", pre + ".to_qkv", self._empty(T, 3 * D), dims=(T, 1, 1, 1), extra=False)
+        a = self.attention(qkv, self._empty(T, D), dim_head=32, n=216, mode=mode, bias_name=pre + ".rel_pos_bias", grid=grid)
+        return self.gemm(a, "lin", pre + ".to_out.0", self._empty(T, D, dtype=x.dtype), dims=(T, 1, 1, 1), extra=False,
+                         out_mode=OUT_F32 if x.dtype == F32 else OUT_BF16, residual=x)
 
     def up_attention_block(self, pre: str, tokens, B: int, grid0, out_last=None):
         """UpAttentionBlock (hybrid_CTUNet.py:554-591); tokens: [B*X*Y*Z, 768] in (x,y,z) order = proj_feat view.
@@ -373,23 +819,19 @@ class Engine:
             p = f"{pre}layers.{ind}.0"
             f = DS_STRIDE[::-1][ind]
             T, D = x.shape
-            xb = self._empty(T, D)  # bf16 stage output feeding the pixel-shuffle GEMM
-            # the stage input is also a returned feature map (or the caller's tokens): the first residual update
-            # goes to a fresh buffer, later ones are in place
-            fresh = self._empty(T, D, dtype=x.dtype)
             if ind <= 2:
-                x = self.window_attention(p + ".1.fn", x, (B, X, Y, Z), 1, out=fresh)
-                self.ffn(p + ".2.fn", x)
-                self.window_attention(p + ".5.fn", x, (B, X, Y, Z), 2)
-                self.ffn(p + ".6.fn", x, out=xb)
-                ps = self.w.pixel_shuffle(p + ".8.to_out", f)
+                x = self.window_attention(p + ".1.fn", x, (B, X, Y, Z), 1)
+                x = self.ffn(p + ".2.fn", x)
+                x = self.window_attention(p + ".5.fn", x, (B, X, Y, Z), 2)
+                xb = self.ffn(p + ".6.fn", x, out_dtype=BF16)
+                ps_name = p + ".8.to_out"
             else:
-                x = self.ffn(p + ".1.fn", x, out=fresh)
-                self.ffn(p + ".2.fn", x, out=xb)
-                ps = self.w.pixel_shuffle(p + ".4.to_out", f)
-            out = out_last if (ind == 3 and out_last is not None) else None
-            y = self.up_gemm(xb.view(B, X, Y, Z, D), ps, out=out)
-            feats.append(y if out is None else out)
+                x = self.ffn(p + ".1.fn", x)
+                xb = self.ffn(p + ".2.fn", x, out_dtype=BF16)
+                ps_name = p + ".4.to_out"
+            out = out_last if ind == 3 else None
+            y = self.up_gemm(xb.view(B, X, Y, Z, D), "ps", ps_name, extra=f, out=out)
+            feats.append(y)
             X, Y, Z = X * f[0], Y * f[1], Z * f[2]
             x = y.reshape(B * X * Y * Z, -1) if out is None else None
         return feats
@@ -399,11 +841,14 @@ class Engine:
         B, _, X, Y, Z = x_in.shape
         tokens, n = self.vit("vit.", x_in, pf, depth, heads)
         cat = self._empty(B, X, Y, Z, 128)  # torch.cat((vit_enc_96x96, vit_enc0), dim=1) built in place
-        self.res_block_cin1("vit_encoder0.layer", x_in, out=cat[..., 64:])
-        enc = self.up_attention_block("vit_encoder.", tokens, B, (X // 16, Y // 16, Z // pf), out_last=cat[..., :64])
+        lo, hi = cat[..., :64], cat[..., 64:]
+        self._alias(lo, cat, 0)
+        self._alias(hi, cat, 64)
+        self.res_block_cin1("vit_encoder0.layer", x_in, out=hi)
+        enc = self.up_attention_block("vit_encoder.", tokens, B, (X // 16, Y // 16, Z // pf), out_last=lo)
         vit_out = self.res_block("vit_decoder0.conv_block", cat, 128, 64)
-        vit_logits = self.head(vit_out, self.w.conv1("vit_out.conv.conv", bias=True))
-        vit_96 = self.head(cat[..., :64], self.w.linear("decoder_linear_96x96.head"), a_c=64)
+        vit_logits = self.head(vit_out, "conv1", "vit_out.conv.conv")
+        vit_96 = self.head(lo, "lin", "decoder_linear_96x96.head", a_c=64)
         return enc, vit_logits, vit_96
 
     def ctunet(self, x_in, layers, pf: int, depth: int = 12, heads: int = 12):
@@ -414,11 +859,11 @@ class Engine:
         dec3 = self.up_2fusion("res_decoder3", res[3], res[2], enc[0], 512)
         dec2 = self.up_2fusion("res_decoder2", dec3, res[1], enc[1], 256)
         dec1 = self.up_2fusion("res_decoder1", dec2, res[0], enc[2], 128)
-        up0 = self.up_gemm(dec1, self.w.convt("res_decoder0.transp_conv.conv"))
+        up0 = self.up_gemm(dec1, "convt", "res_decoder0.transp_conv.conv")
         res_out = self.res_block("res_decoder0.conv_block", up0, 64, 64)
-        res_logits = self.head(res_out, self.w.conv1("res_out.conv.conv", bias=True))
-        res_48 = self.head(dec1, self.w.conv1("res_out_48x48.conv.conv", bias=True))
-        res_24 = self.head(dec2, self.w.conv1("res_out_24x24.conv.conv", bias=True))
+        res_logits = self.head(res_out, "conv1", "res_out.conv.conv")
+        res_48 = self.head(dec1, "conv1", "res_out_48x48.conv.conv")
+        res_24 = self.head(dec2, "conv1", "res_out_24x24.conv.conv")
         return ((res_logits, res_48, res_24), (vit_logits, vit_96))
 
     def tunet(self, x_in, pf: int, depth: int = 12, heads: int = 12):
@@ -431,8 +876,11 @@ class Engine:
         """UpCatConvBlock (hybrid_CTUNet.py:196-201): ConvT -> cat(skip) -> ResBlock(2C -> C)."""
         B, X, Y, Z, _ = skip.shape
         cat = self._empty(B, X, Y, Z, 2 * cout)
-        self.up_gemm(inp, self.w.convt(pre + ".transp_conv.conv"), out=cat[..., :cout])
-        ops.subsample(skip, cat[..., cout:], (1, 1, 1))  # stride-1 gather == strided copy into the concat buffer
+        lo, hi = cat[..., :cout], cat[..., cout:]
+        self._alias(lo, cat, 0)
+        self._alias(hi, cat, cout)
+        self.up_gemm(inp, "convt", pre + ".transp_conv.conv", out=lo)
+        self.subsample(skip, hi, (1, 1, 1))  # stride-1 gather == strided copy into the concat buffer
         return self.res_block(pre + ".conv_block", cat, 2 * cout, cout)
 
     def cunet(self, x_in, layers):
@@ -442,8 +890,8 @@ class Engine:
         dec3 = self.up_cat_conv("res_decoder3", res[3], res[2], 512)
         dec2 = self.up_cat_conv("res_decoder2", dec3, res[1], 256)
         dec1 = self.up_cat_conv("res_decoder1", dec2, res[0], 128)
-        up0 = self.up_gemm(dec1, self.w.convt("res_decoder0.transp_conv.conv"))
+        up0 = self.up_gemm(dec1, "convt", "res_decoder0.transp_conv.conv")
         res_out = self.res_block("res_decoder0.conv_block", up0, 64, 64)
-        return (self.head(res_out, self.w.conv1("res_out.conv.conv", bias=True)),
-                self.head(dec1, self.w.conv1("res_out_48x48.conv.conv", bias=True)),
-                self.head(dec2, self.w.conv1("res_out_24x24.conv.conv", bias=True)))
+        return (self.head(res_out, "conv1", "res_out.conv.conv"),
+                self.head(dec1, "conv1", "res_out_48x48.conv.conv"),
+                self.head(dec2, "conv1", "res_out_24x24.conv.conv"))

@@ -1,5 +1,8 @@
-"""Shared plumbing of the drop-in modules: engine construction and layout conversion at block boundaries."""
+"""Shared plumbing of the drop-in modules: engine construction, layout conversion at block boundaries and the
+autograd bridge that makes every module trainable (trainer_CTUNet.py:87-109 calls loss.backward() through them)."""
 from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
@@ -19,9 +22,67 @@ def from_cl(x: torch.Tensor) -> torch.Tensor:
     return x.permute(0, 4, 1, 2, 3).float().contiguous()
 
 
+class Program:
+    """What one module forward hands to the autograd bridge.
+
+    in_acts : per module input, the engine-side tensor its gradient is read from (None: no gradient, e.g. the image)
+    out_acts: engine-side output tensors (channels-last bf16 maps, or tensors returned as they are)
+    outputs : what the caller receives, one per out_act (from_cl(out_act) when `converted`)
+    """
+
+    def __init__(self, in_acts: Sequence[Optional[torch.Tensor]], out_acts: Sequence[torch.Tensor], converted: bool = True):
+        self.in_acts = list(in_acts)
+        self.out_acts = list(out_acts)
+        self.converted = converted
+        self.outputs = [from_cl(o) for o in out_acts] if converted else list(out_acts)
+
+
+class _EngineFn(torch.autograd.Function):
+    """Runs a module's engine program with the tape on; backward replays the tape (Engine.backward)."""
+
+    @staticmethod
+    def forward(ctx, module, n_in, *tensors):
+        eng = module._engine()
+        eng.begin_training_forward()
+        try:
+            prog = module._program(eng, *[t.detach() for t in tensors[:n_in]])
+        except Exception:
+            eng.tape = None
+            raise
+        ctx.module, ctx.eng, ctx.tape, ctx.prog, ctx.n_in = module, eng, eng.tape, prog, n_in
+        ctx.stats = eng.stats
+        ctx.in_shapes = [t.shape for t in tensors[:n_in]]
+        ctx.names = [n for n, _ in module.named_parameters()]
+        eng.tape = None  # a later inference call on the same module must not extend this tape
+        return tuple(prog.outputs)
+
+    @staticmethod
+    def backward(ctx, *grad_outputs):
+        eng, prog = ctx.eng, ctx.prog
+        eng.tape, eng.stats = ctx.tape, ctx.stats
+        seeds = []
+        for act, g in zip(prog.out_acts, grad_outputs):
+            if g is not None and prog.converted:
+                g = to_cl(g)
+            seeds.append((act, g))
+        pgrads, igrads = eng.backward(seeds, want=prog.in_acts)
+        outs: List[Optional[torch.Tensor]] = [None, None]
+        for act, g, shp, need in zip(prog.in_acts, igrads, ctx.in_shapes, ctx.needs_input_grad[2:2 + ctx.n_in]):
+            if g is None or not need:
+                outs.append(None)
+            elif g.dim() == 5 and len(shp) == 5:  # channels-last activation gradient -> NCDHW fp32
+                outs.append(from_cl(g))
+            else:
+                outs.append(g.float().reshape(shp))
+        for name in ctx.names:
+            outs.append(pgrads.get(name))
+        ctx.tape = ctx.prog = None
+        return tuple(outs)
+
+
 class KernelModule(nn.Module):
-    """nn.Module whose forward runs on the sm_100a kernels.  There is no CPU / eager fallback: calling it
-    without a CUDA tensor or without the built library raises."""
+    """nn.Module whose forward (and backward) runs on the sm_100a kernels.  There is no CPU / eager fallback:
+    calling it without a CUDA tensor or without the built library raises."""
 
     def _engine(self) -> Engine:
         params = dict(self.named_parameters())
@@ -41,7 +102,21 @@ class KernelModule(nn.Module):
     def _input(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:
             raise CtuError("input must be a CUDA tensor (no CPU fallback)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise CtuError("the backward path is not implemented yet: call under torch.no_grad() / model.eval() "
-                           "with torch.inference_mode()")
         return x.float().contiguous()
+
+    def _program(self, eng: Engine, *inputs) -> Program:
+        raise NotImplementedError
+
+    def _call(self, *inputs: torch.Tensor) -> Tuple[torch.Tensor, ...]:
+        """Run the module's program: through the autograd bridge when a gradient may be needed, plainly otherwise."""
+        for x in inputs:
+            if not x.is_cuda:
+                raise CtuError("input must be a CUDA tensor (no CPU fallback)")
+        needs = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
+                                             any(x.requires_grad for x in inputs))
+        if needs:
+            return _EngineFn.apply(self, len(inputs), *inputs, *self.parameters())
+        eng = self._engine()
+        eng.tape = None
+        with torch.no_grad():
+            return tuple(self._program(eng, *inputs).outputs)

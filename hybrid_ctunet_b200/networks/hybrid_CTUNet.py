@@ -13,7 +13,7 @@ from typing import Sequence, Tuple, Union
 import torch
 import torch.nn as nn
 
-from ._base import KernelModule, from_cl, to_cl
+from ._base import KernelModule, Program, from_cl, to_cl
 from .resnet import ConvHolder, generate_model as resnet
 from .resnet import get_conv_layer
 from .vit import ViT, _no_dropout
@@ -41,13 +41,16 @@ class ResBlock(KernelModule):
         self.in_channels, self.out_channels = in_channels, out_channels
         self.downsample = in_channels != out_channels
 
-    def forward(self, inp):
-        eng = self._engine()
+    def _program(self, eng, inp):
         eng.stats.reset()
         x = self._input(inp)
         if self.in_channels == 1:
-            return from_cl(eng.res_block_cin1("", x))
-        return from_cl(eng.res_block("", to_cl(x), self.in_channels, self.out_channels))
+            return Program([None], [eng.res_block_cin1("", x)])
+        a = to_cl(x)
+        return Program([a], [eng.res_block("", a, self.in_channels, self.out_channels)])
+
+    def forward(self, inp):
+        return self._call(inp)[0]
 
 
 class BasicConvBlock(KernelModule):
@@ -71,10 +74,13 @@ class UpCatConvBlock(KernelModule):
         self.conv_block = ResBlock(spatial_dims, out_channels + out_channels, out_channels, kernel_size, 1, norm_name)
         self.out_channels = out_channels
 
-    def forward(self, inp, skip):
-        eng = self._engine()
+    def _program(self, eng, inp, skip):
         eng.stats.reset()
-        return from_cl(eng.up_cat_conv("", to_cl(self._input(inp)), to_cl(self._input(skip)), self.out_channels))
+        a, b = to_cl(self._input(inp)), to_cl(self._input(skip))
+        return Program([a, b], [eng.up_cat_conv("", a, b, self.out_channels)])
+
+    def forward(self, inp, skip):
+        return self._call(inp, skip)[0]
 
 
 class UpConvBlock(KernelModule):
@@ -87,11 +93,14 @@ class UpConvBlock(KernelModule):
         self.conv_block = ResBlock(spatial_dims, out_channels, out_channels, kernel_size, 1, norm_name)
         self.out_channels = out_channels
 
-    def forward(self, inp):
-        eng = self._engine()
+    def _program(self, eng, inp):
         eng.stats.reset()
-        up = eng.up_gemm(to_cl(self._input(inp)), eng.w.convt("transp_conv.conv"))
-        return from_cl(eng.res_block("conv_block", up, self.out_channels, self.out_channels))
+        a = to_cl(self._input(inp))
+        up = eng.up_gemm(a, "convt", "transp_conv.conv")
+        return Program([a], [eng.res_block("conv_block", up, self.out_channels, self.out_channels)])
+
+    def forward(self, inp):
+        return self._call(inp)[0]
 
 
 class pixelweight_attention(KernelModule):
@@ -112,9 +121,12 @@ class pixelweight_attention(KernelModule):
         self.attend = nn.Sequential(nn.Softmax(dim=-1), nn.Dropout(dropout))
         self.to_out = nn.Sequential(nn.Linear(dim, dim, bias=False), nn.Dropout(dropout))
 
+    def _program(self, eng, x1, x2):
+        a, b = to_cl(self._input(x1)), to_cl(self._input(x2))
+        return Program([a, b], [eng.pixelweight_attention("", a, b)])
+
     def forward(self, x1, x2):
-        eng = self._engine()
-        return from_cl(eng.pixelweight_attention("", to_cl(self._input(x1)), to_cl(self._input(x2))))
+        return self._call(x1, x2)[0]
 
 
 class Up_2Fusion_Block(KernelModule):
@@ -130,15 +142,16 @@ class Up_2Fusion_Block(KernelModule):
         self.up_addconv_block2 = ResBlock(spatial_dims, out_channels, out_channels, kernel_size, 1, norm_name)
         self.out_channels = out_channels
 
+    def _program(self, eng, inp, skip_conv, skip_vit):
+        eng.stats.reset()
+        a, b, c = to_cl(self._input(inp)), to_cl(self._input(skip_conv)), to_cl(self._input(skip_vit))
+        return Program([a, b, c], [eng.up_2fusion("", a, b, c, self.out_channels)])
+
     def forward(self, inp, skip_conv=None, skip_vit=None):
         if skip_vit is None:
             # the reference raises NameError here (hybrid_CTUNet.py:332-338: `skip` is unbound)
             raise NameError("name 'skip' is not defined")
-        eng = self._engine()
-        eng.stats.reset()
-        out = eng.up_2fusion("", to_cl(self._input(inp)), to_cl(self._input(skip_conv)), to_cl(self._input(skip_vit)),
-                             self.out_channels)
-        return from_cl(out)
+        return self._call(inp, skip_conv, skip_vit)[0]
 
 
 class PixelShuffle(KernelModule):
@@ -155,8 +168,11 @@ class PixelShuffle(KernelModule):
         if x.shape[1] % div != 0:
             raise ValueError(f"Number of input channels ({x.shape[1]}) must be evenly"
                              f"divisibel by scale_factor ** dimensions ({self.scale_factor}**{self.spatial_dims}={div}).")
-        eng = self._engine()
-        return from_cl(eng.up_gemm(to_cl(self._input(x)), eng.w.pixel_shuffle("to_out", tuple(self.scale_factor))))
+        return self._call(x)[0]
+
+    def _program(self, eng, x):
+        a = to_cl(self._input(x))
+        return Program([a], [eng.up_gemm(a, "ps", "to_out", extra=tuple(self.scale_factor))])
 
 
 class Residual(nn.Module):
@@ -228,11 +244,12 @@ class UpAttentionBlock(KernelModule):
 
     def forward(self, x):
         """x: [B, 768, X, Y, Z] -> [x, 512@2x, 256@4x, 128@8x, 64@(16,16,8)x] like hybrid_CTUNet.py:585-591."""
-        eng = self._engine()
+        return [x] + list(self._call(x))
+
+    def _program(self, eng, x):
         B, C, X, Y, Z = x.shape
         tokens = self._input(x).permute(0, 2, 3, 4, 1).reshape(B * X * Y * Z, C).contiguous()
-        feats = eng.up_attention_block("", tokens, B, (X, Y, Z))
-        return [x] + [from_cl(f) for f in feats]
+        return Program([tokens.view(B, X, Y, Z, C)], eng.up_attention_block("", tokens, B, (X, Y, Z)))
 
 
 class CatConvBlock(KernelModule):
@@ -243,11 +260,17 @@ class CatConvBlock(KernelModule):
         self.conv_block = ResBlock(spatial_dims, in_channels + in_channels, in_channels, kernel_size, 1, norm_name)
         self.in_channels = in_channels
 
-    def forward(self, x, skip):
-        eng = self._engine()
+    def _program(self, eng, x, skip):
         eng.stats.reset()
+        C = self.in_channels
         cat = torch.cat((to_cl(self._input(x)), to_cl(self._input(skip))), dim=-1)
-        return from_cl(eng.res_block("conv_block", cat, 2 * self.in_channels, self.in_channels))
+        lo, hi = cat[..., :C], cat[..., C:]
+        eng._alias(lo, cat, 0)
+        eng._alias(hi, cat, C)
+        return Program([lo, hi], [eng.res_block("conv_block", cat, 2 * C, C)])
+
+    def forward(self, x, skip):
+        return self._call(x, skip)[0]
 
 
 class DecoderLinear(KernelModule):
@@ -266,10 +289,13 @@ class DecoderLinear(KernelModule):
         F_, H, W = im_size
         if self.patch_size != 1:
             raise NotImplementedError("CTUNet uses DecoderLinear with patch_size 1")
-        eng = self._engine()
-        b = x.shape[0]
-        cl = self._input(x).to(torch.bfloat16).reshape(b, F_, H, W, self.d_encoder)
-        return eng.head(cl, eng.w.linear("head"))
+        object.__setattr__(self, "_im_size", (F_, H, W))
+        return self._call(x)[0]
+
+    def _program(self, eng, x):
+        F_, H, W = self._im_size
+        cl = self._input(x).to(torch.bfloat16).reshape(x.shape[0], F_, H, W, self.d_encoder)
+        return Program([cl], [eng.head(cl, "lin", "head")], converted=False)
 
 
 class UnetOutBlock(KernelModule):
@@ -279,9 +305,12 @@ class UnetOutBlock(KernelModule):
         super().__init__()
         self.conv = get_conv_layer(spatial_dims, in_channels, out_channels, kernel_size=1, stride=1, bias=True)
 
+    def _program(self, eng, inp):
+        a = to_cl(self._input(inp))
+        return Program([a], [eng.head(a, "conv1", "conv.conv")], converted=False)
+
     def forward(self, inp):
-        eng = self._engine()
-        return eng.head(to_cl(self._input(inp)), eng.w.conv1("conv.conv", bias=True))
+        return self._call(inp)[0]
 
 
 class _Net(KernelModule):
@@ -320,12 +349,23 @@ class _Net(KernelModule):
         ent["graph"].replay()
         return ent["out"]
 
+    def _program(self, eng, x_in):
+        outs = self._run(eng, self._input(x_in))
+        flat = [t for grp in outs for t in (grp if isinstance(grp, (tuple, list)) else (grp,))]
+        return Program([None], flat, converted=False)
+
+    def _nest(self, flat):
+        """Flat logits tuple -> the reference's return structure."""
+        return tuple(flat)
+
     def forward(self, x_in):
-        x = self._input(x_in)
-        eng = self._engine()
-        if getattr(self, "_use_graph", False):
-            return self._graph_forward(eng, x)
-        return self._run(eng, x)
+        training = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if getattr(self, "_use_graph", False) and not training:
+            eng = self._engine()
+            eng.tape = None
+            with torch.no_grad():
+                return self._graph_forward(eng, self._input(x_in))
+        return self._nest(self._call(x_in))
 
 
 class CTUNet(_Net):
@@ -370,6 +410,9 @@ class CTUNet(_Net):
 
     def _run(self, eng, x):
         return eng.ctunet(x, self.convnet.block_counts, self.patch_frame, self.num_depths, self.num_heads)
+
+    def _nest(self, flat):
+        return ((flat[0], flat[1], flat[2]), (flat[3], flat[4]))
 
 
 class CUNet(_Net):

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ._base import KernelModule, from_cl, to_cl
+from ._base import KernelModule, Program, from_cl, to_cl
 
 
 def get_inplanes():
@@ -80,11 +80,13 @@ class Bottleneck(KernelModule):
         self.downsample = downsample
         self.stride = stride
 
-    def forward(self, x):
-        eng = self._engine()
+    def _program(self, eng, x):
         eng.stats.reset()
-        out = eng.bottleneck("", to_cl(self._input(x)), _triple(self.stride), self.downsample is not None)
-        return from_cl(out)
+        a = to_cl(self._input(x))
+        return Program([a], [eng.bottleneck("", a, _triple(self.stride), self.downsample is not None)])
+
+    def forward(self, x):
+        return self._call(x)[0]
 
 
 class ResNet(KernelModule):
@@ -120,11 +122,12 @@ class ResNet(KernelModule):
             mods.append(block(self.in_planes, planes))
         return nn.Sequential(*mods)
 
-    def forward(self, x):
-        eng = self._engine()
+    def _program(self, eng, x):
         eng.stats.reset()
-        feats = eng.resnet("", self._input(x), self.block_counts)
-        return [from_cl(f) for f in feats]
+        return Program([None], eng.resnet("", self._input(x), self.block_counts))
+
+    def forward(self, x):
+        return list(self._call(x))
 
 
 def generate_model(model_depth, **kwargs):

@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from ._base import KernelModule
+from ._base import KernelModule, Program
 
 
 def pair(t):
@@ -40,13 +40,13 @@ class FeedForward(KernelModule):
         self.net = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, hidden_dim), nn.GELU(), nn.Dropout(dropout),
                                  nn.Linear(hidden_dim, dim), nn.Dropout(dropout))
 
+    def _program(self, eng, x):
+        t = self._input(x).reshape(-1, x.shape[-1])
+        return Program([t], [eng.ffn("", t)], converted=False)
+
     def forward(self, x):
         """Returns net(x) (without the residual), like vit.py:43-44."""
-        eng = self._engine()
-        shp = x.shape
-        t = self._input(x).reshape(-1, shp[-1]).clone()
-        y = eng.ffn("", t)
-        return (y - self._input(x).reshape(-1, shp[-1])).reshape(shp)
+        return self._call(x)[0].reshape(x.shape) - x
 
 
 class Attention(KernelModule):
@@ -64,14 +64,14 @@ class Attention(KernelModule):
         self.to_qkv = nn.Linear(dim, inner_dim * 3, bias=False)
         self.to_out = nn.Sequential(nn.Linear(inner_dim, dim), nn.Dropout(dropout))
 
+    def _program(self, eng, x):
+        b, n, d = x.shape
+        t = self._input(x).reshape(b * n, d)
+        return Program([t], [eng.vit_attention("", t, b, n, self.heads)], converted=False)
+
     def forward(self, x):
         """Returns the attention branch (without the residual), like vit.py:66-78."""
-        eng = self._engine()
-        b, n, d = x.shape
-        x0 = self._input(x).reshape(b * n, d)
-        t = x0.clone()
-        eng.vit_attention("", t, b, n, self.heads)
-        return (t - x0).reshape(b, n, d)
+        return self._call(x)[0].reshape(x.shape) - x
 
 
 class TransformerBlock(KernelModule):
@@ -82,13 +82,13 @@ class TransformerBlock(KernelModule):
         self.drop_path = DropPath(dropout) if drop_path > 0.0 else nn.Identity()
         self.heads = heads
 
-    def forward(self, x):
-        eng = self._engine()
+    def _program(self, eng, x):
         b, n, d = x.shape
-        t = self._input(x).reshape(b * n, d).clone()
-        eng.vit_attention("attn", t, b, n, self.heads)
-        eng.ffn("ff", t)
-        return t.reshape(b, n, d)
+        t = self._input(x).reshape(b * n, d)
+        return Program([t], [eng.ffn("ff", eng.vit_attention("attn", t, b, n, self.heads))], converted=False)
+
+    def forward(self, x):
+        return self._call(x)[0].reshape(x.shape)
 
 
 class ViT(KernelModule):
@@ -116,7 +116,9 @@ class ViT(KernelModule):
         self.frame_patch_size = frame_patch_size
         self.depth, self.heads, self.dim = depth, heads, dim
 
+    def _program(self, eng, img):
+        x, _ = eng.vit("", self._input(img), self.frame_patch_size, self.depth, self.heads)
+        return Program([None], [x], converted=False)
+
     def forward(self, img):
-        eng = self._engine()
-        x, n = eng.vit("", self._input(img), self.frame_patch_size, self.depth, self.heads)
-        return x.view(img.shape[0], n, self.dim)
+        return self._call(img)[0].view(img.shape[0], -1, self.dim)

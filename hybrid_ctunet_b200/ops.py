@@ -407,13 +407,13 @@ def im2col_cin1(x: torch.Tensor, out: torch.Tensor, *, k, s, p) -> torch.Tensor:
 
 
 def accumulate(src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
-    """dst += src for [.., C] tensors with arbitrary row strides (same dtype, bf16 or fp32)."""
+    """dst += src for [.., C] tensors with arbitrary row strides; src / dst independently bf16 or fp32."""
     lib = _lib.require_device()
-    assert src.dtype == dst.dtype and src.shape == dst.shape
+    assert src.numel() == dst.numel() and src.shape[-1] == dst.shape[-1]
     C_ = src.shape[-1]
     M = src.numel() // C_
-    check(lib.ctu_accumulate(src.data_ptr(), int(src.stride(-2)), dst.data_ptr(), int(dst.stride(-2)), M, C_,
-                             int(src.dtype == torch.float32), _stream()), "ctu_accumulate")
+    check(lib.ctu_accumulate(src.data_ptr(), int(src.dtype == torch.float32), int(src.stride(-2)), dst.data_ptr(),
+                             int(dst.dtype == torch.float32), int(dst.stride(-2)), M, C_, _stream()), "ctu_accumulate")
     return dst
 
 

@@ -198,8 +198,9 @@ int ctu_subsample_bwd(const void* dsub, int lds, void* dfull, int ldf, int i1, i
 int ctu_im2col_cin1(const float* img, void* out, int B, int X, int Y, int Z, int kx, int ky, int kz, int sx, int sy,
                     int sz, int px, int py, int pz, int kpad, void* stream);
 
-/* dst[row][0..C) += src[row][0..C) (bf16 or fp32 rows); dst(bf16) = src(fp32). */
-int ctu_accumulate(const void* src, long long lds, void* dst, long long ldd, long long M, int C, int is_f32, void* stream);
+/* dst[row][0..C) += src[row][0..C), src and dst independently bf16 or fp32 rows (C % 8 == 0); dst(bf16) = src(fp32). */
+int ctu_accumulate(const void* src, int src_is_f32, long long lds, void* dst, int dst_is_f32, long long ldd, long long M,
+                   int C, void* stream);
 int ctu_cast_f32_bf16(const float* src, long long lds, void* dst, long long ldd, long long M, int C, void* stream);
 
 /* dgamma / dbeta (fp32 [256*pf], accumulated) of the LayerNorm fused into ctu_patchify_ln. */
