@@ -1,19 +1,21 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native CTUNet hot path.
 
-Workload (BASELINE.json configs[2], the largest single-GPU configuration whose every kernel is ours end to end):
-sliding-window inference of one synthetic 1x1x512x512x256 volume with CTUNet(depth 101, patch_frame 8), 96^3
-windows, overlap 0.5, Gaussian blend, sw_batch 4, both heads blended.  One step = one whole volume (500 windows =
-125 network calls + 1000 blend launches + normalise).  With --gpus N the 500 windows are split into N contiguous
-chunks (one process per GPU) and the two fp32 accumulators are summed with one NCCL all-reduce each: total work is
-fixed, so scaling is "strong".
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): one CTUNet(depth 101, patch_frame 8)
+TRAINING STEP on synthetic 96^3 patches, batch 2 per GPU, bf16 activations / fp32 weight gradients: forward, the
+reference's five-head Dice-CE loss (trainer_CTUNet.py:92-103), backward through every kernel of this repo, gradient
+all-reduce over NCCL when N > 1 (data parallel, main_CTUNet.py:187-189) and the AdamW update (main_CTUNet.py:190-193).
+`value` = 96^3 patches/s over all ranks (weak scaling: 2 patches per GPU per step).  The second half of the metric —
+whole-volume sliding-window inference volumes/s (configs[2]: 512x512x256, 96^3 windows, overlap 0.5, Gaussian blend,
+windows sharded over the ranks with one NCCL all-reduce per head) — is measured in the same run and reported under
+"sliding_window".
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-sliding-window]
 
-Prints ONE JSON line (rank 0).  `value` is volumes/s with the volume resident in HBM; `e2e` is the same metric
-through the public API with the volume in pinned host memory (H2D inside the timed region) and both blended
-logit volumes read back to the host.  `--impl reference` times the reference's CPU path (the fp32 oracle
-restatement, oracle/) on the host cores on a bounded sample and extrapolates.
+Prints ONE JSON line (rank 0).  `e2e` is the same training step driven through the public API from pinned HOST
+buffers (H2D of the patches and labels inside the timed region, loss read back to the host every step).
+`--impl reference` times the reference's own CPU path (fp32 oracle restatement of the modules + loss + torch autograd)
+on the host cores, one 96^3 patch per step.
 """
 from __future__ import annotations
 
@@ -31,14 +33,12 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-VOLUME = (512, 512, 256)
-ROI = (96, 96, 96)
-OVERLAP = 0.5
-SW_BATCH = 4
-NUM_WINDOWS = 500
 KW = dict(in_channels=1, dim_conv_stem=64, out_channels=14, model_depth=101, img_size=(96, 96), frames=96, patch_frame=8)
-FWD_GFLOP_PER_WINDOW = 3423.64  # SURVEY 8d [probe]: CTUNet forward, one 96^3 patch
-WORKLOAD = "sliding_window 1x1x512x512x256, CTUNet(101,pf8), roi 96^3, overlap 0.5, gaussian, sw_batch 4, 2 heads"
+BATCH_PER_GPU = 2
+FWD_BWD_GFLOP_PER_PATCH = 10258.03  # SURVEY 8d [probe]
+FWD_GFLOP_PER_PATCH = 3423.64
+WORKLOAD = "CTUNet(101,pf8) training step (fwd + 5-head Dice-CE + bwd + AdamW), 96^3 patches, batch 2/GPU, bf16"
+VOLUME, ROI, OVERLAP, SW_BATCH, NUM_WINDOWS = (512, 512, 256), (96, 96, 96), 0.5, 4, 500
 
 
 def _peaks():
@@ -92,7 +92,9 @@ class ClockSampler:
 
 
 class ConvProbe:
-    """CUDA events around every launch of the dominant kernel (3x3x3 conv 64->64 at 96^3) inside the timed region."""
+    """CUDA events around every launch of the dominant kernel inside the timed region: the tcgen05 implicit-GEMM
+    3x3x3 convolution 64 -> 64 channels at 96^3 (forward AND input-gradient launches use the same kernel; 4 forward +
+    4 dgrad launches per step, 1.57 TFLOP each at batch 2)."""
 
     def __init__(self):
         self.pairs, self.flops = [], 0.0
@@ -125,84 +127,67 @@ class ConvProbe:
         ms = [a.elapsed_time(b) for a, b in self.pairs]
         avg = sum(ms) / len(ms)
         ach = self.flops / (avg * 1e-3) / 1e12
-        return {"bound": "tensor", "kernel": "umma_gemm_kernel<64,4> as conv3x3x3 64->64 @96^3 x4 windows",
+        return {"bound": "tensor", "kernel": "umma_gemm_kernel<64,...> as conv3x3x3 64->64 @96^3 (forward + dgrad launches)",
                 "achieved": round(ach, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": round(ach / peaks["tf_sustained"], 4), "traffic": None, "launches_timed": len(ms),
                 "avg_launch_ms": round(avg, 4), "flops_per_launch": self.flops, "peak_source": peaks["src"] + ", sustained"}
 
 
-def cpu_baseline_sample(threads: int):
-    """Reference CPU path on a bounded sample: ONE 96^3 window through the fp32 oracle (CTUNet forward) + the oracle
-    blend of that window, on the host cores; extrapolated to the 500 windows of the volume."""
-    from oracle import ctunet_oracle as O
-    from oracle import sliding_window_oracle as SO
+# --------------------------------------------------------------------------------------------- reference / CPU arm
+def _oracle_train_step_seconds(threads: int, warmup: int, steps: int):
+    """The reference's CPU path for one training step on ONE 96^3 patch: oracle CTUNet fp32 forward + 5-head Dice-CE
+    (scipy zoom labels) + torch autograd backward, all host threads."""
+    from oracle import train_oracle as T
     from hybrid_ctunet_b200.networks.hybrid_CTUNet import CTUNet
     torch.set_num_threads(threads)
     torch.manual_seed(0)
     sd = {k: v.detach() for k, v in CTUNet(**KW).state_dict().items()}
-    torch.manual_seed(2)
-    x = torch.rand(1, 1, 96, 96, 144)
+    torch.manual_seed(1)
+    x = torch.rand(1, 1, 96, 96, 96)
+    y = torch.randint(0, 14, (1, 1, 96, 96, 96)).float()
+    for _ in range(warmup):
+        T.ctunet_train_step(sd, x, y)
     t0 = time.perf_counter()
-    with torch.no_grad():
-        O.ctunet_forward(sd, x[..., :96], 101, 8)  # warm-up of the thread pool / allocator on a full window
-    warm = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        SO.sliding_window_inference(x[..., :96], ROI, SW_BATCH, lambda w: O.ctunet_forward(sd, w, 101, 8), overlap=OVERLAP,
-                                    mode="gaussian", two_heads=True)
-    per_window = time.perf_counter() - t0
-    return per_window, warm
+    for _ in range(steps):
+        T.ctunet_train_step(sd, x, y)
+    return (time.perf_counter() - t0) / steps
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle restatement, kind "port"),
-    each step = one window (forward + blend) on all host threads, extrapolated to volumes/s."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    from oracle import ctunet_oracle as O
-    from oracle import sliding_window_oracle as SO
-    from hybrid_ctunet_b200.networks.hybrid_CTUNet import CTUNet
-    torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    sd = {k: v.detach() for k, v in CTUNet(**KW).state_dict().items()}
-    torch.manual_seed(2)
-    x = torch.rand(1, 1, 96, 96, 96)
-    pred = lambda w: O.ctunet_forward(sd, w, 101, 8)
-    step = lambda: SO.sliding_window_inference(x, ROI, SW_BATCH, pred, overlap=OVERLAP, mode="gaussian", two_heads=True)
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            step()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step()
-        dt = (time.perf_counter() - t0) / args.steps
-    value = 1.0 / (dt * NUM_WINDOWS)
-    sample = "1 of 500 windows per step (CTUNet fp32 forward + Gaussian blend), extrapolated x500"
+    dt = _oracle_train_step_seconds(threads, min(args.warmup, 1), args.steps)
+    value = 1.0 / dt
+    sample = "1 patch (batch 1) per step: oracle CTUNet fp32 fwd + 5-head Dice-CE + autograd bwd on the host cores (1 warm-up)"
     print(json.dumps({
-        "impl": "reference", "metric": "sliding_window_volumes_per_s", "value": value, "unit": "volumes/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 * NUM_WINDOWS,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": "reference", "metric": "train_patches_per_s", "value": value, "unit": "patches/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+# --------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sliding-window", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch.distributed as dist
     from hybrid_ctunet_b200 import lib
+    from hybrid_ctunet_b200.dp import GradientAllReduce
+    from hybrid_ctunet_b200.losses import DiceCELoss, ctunet_loss
     from hybrid_ctunet_b200.networks.hybrid_CTUNet import CTUNet
     from hybrid_ctunet_b200.trainer_CTUNet import sliding_window_inference
 
@@ -218,16 +203,28 @@ def main():
         group = dist.group.WORLD
     lib.require_device()
     peaks = _peaks()
+    warmup = max(args.warmup, 3)
+    B = BATCH_PER_GPU
 
     torch.manual_seed(0)
-    model = CTUNet(**KW).to(dev).eval()
-    torch.manual_seed(2)
-    host_vol = torch.rand(1, 1, *VOLUME).pin_memory()
-    vol = host_vol.to(dev, non_blocking=True)
+    model = CTUNet(**KW).to(dev).train()
+    loss_func = DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)
+    reducer = GradientAllReduce(model.parameters(), group) if world > 1 else None
+    torch.manual_seed(1 + rank)
+    host_x = torch.rand(B, 1, 96, 96, 96).pin_memory()
+    host_y = torch.randint(0, 14, (B, 1, 96, 96, 96)).float().pin_memory()
+    x, y = host_x.to(dev), host_y.to(dev)
 
-    def step(v):
-        with torch.no_grad():
-            return sliding_window_inference(v, ROI, SW_BATCH, model, overlap=OVERLAP, mode="gaussian", shard_group=group)
+    def train_step(xd, yd):
+        for p in model.parameters():
+            p.grad = None
+        loss = ctunet_loss(model(xd), yd, loss_func)
+        loss.backward()
+        if reducer is not None:
+            reducer.reduce()
+        opt.step()
+        return loss
 
     def sync():
         torch.cuda.synchronize()
@@ -235,9 +232,14 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        out = step(vol)
-    del out
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(warmup):
+        train_step(x, y)
     sync()
 
     # ---------------- device-resident timing (value) with the dominant-kernel probe and clock sampling
@@ -249,58 +251,85 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            out = step(vol)
+            loss = train_step(x, y)
         e1.record()
         sync()
     probe.remove()
-    launches = lib.launch_count() - n0
-    ms = e0.elapsed_time(e1) / args.steps
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    del out
+    launches = (lib.launch_count() - n0) / args.steps
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    loss_value = float(loss.detach())
 
-    # ---------------- end to end through the public API: pinned host volume in, blended logits out to the host
-    host_out = [torch.empty((1, 14) + VOLUME, dtype=torch.float32).pin_memory() for _ in range(2)] if rank == 0 else None
+    # ---------------- end to end through the public API: pinned host patches + labels in, loss out, every step
     sync()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(args.steps):
-        v = host_vol.to(dev, non_blocking=True)
-        o = step(v)
-        if rank == 0:
-            host_out[0].copy_(o[0], non_blocking=True)
-            host_out[1].copy_(o[1], non_blocking=True)
-        del o
+        xd, yd = host_x.to(dev, non_blocking=True), host_y.to(dev, non_blocking=True)
+        _ = train_step(xd, yd).item()
     f1.record()
     sync()
-    t = torch.tensor([f0.elapsed_time(f1) / args.steps], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks(f0.elapsed_time(f1) / args.steps)
+    peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
+
+    # ---------------- second half of the metric: sliding-window inference of one 512x512x256 volume
+    sw = None
+    if not args.no_sliding_window:
+        model.eval()
+        for p in model.parameters():
+            p.grad = None
+        del opt
+        torch.cuda.empty_cache()
+        torch.manual_seed(2)
+        host_vol = torch.rand(1, 1, *VOLUME).pin_memory()
+        vol = host_vol.to(dev)
+
+        def infer(v):
+            with torch.no_grad():
+                return sliding_window_inference(v, ROI, SW_BATCH, model, overlap=OVERLAP, mode="gaussian", shard_group=group)
+
+        out = infer(vol)
+        del out
+        sync()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        out = infer(vol)
+        g1.record()
+        sync()
+        sw_ms = max_over_ranks(g0.elapsed_time(g1))
+        del out
+        sw = {"metric": "sliding_window_volumes_per_s", "value": 1e3 / sw_ms, "unit": "volumes/s", "ms_per_volume": sw_ms,
+              "scaling": "strong", "windows": NUM_WINDOWS, "warmup": 1, "steps": 1,
+              "workload": "1x1x512x512x256, roi 96^3, overlap 0.5, gaussian, sw_batch 4, 2 heads",
+              "tflops_per_gpu": NUM_WINDOWS * FWD_GFLOP_PER_PATCH / sw_ms / world,
+              "parallelism": f"windows sharded over {world} GPU(s), 1 NCCL all-reduce per head" if world > 1 else "single GPU"}
 
     if rank == 0:
+        patches = B * world
         line = {
-            "metric": "sliding_window_volumes_per_s", "value": 1e3 / ms, "unit": "volumes/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "windows": NUM_WINDOWS, "l2": "activations (>=0.9 GB per layer) exceed the 126 MB L2",
-                       "parallelism": f"windows sharded over {world} GPU(s), 1 all-reduce per head" if world > 1 else "single GPU",
-                       "launch_mode": "eager launches (CUDA-graph replay is available via enable_cuda_graph)"},
-            "tflops_per_gpu": NUM_WINDOWS * FWD_GFLOP_PER_WINDOW / ms / world,
-            "e2e": {"value": 1e3 / e2e_ms, "unit": "volumes/s", "h2d_bytes_per_step": host_vol.numel() * 4,
-                    "d2h_bytes_per_step": 2 * 14 * VOLUME[0] * VOLUME[1] * VOLUME[2] * 4, "ms_per_step": e2e_ms},
-            "gpu_launches": int(launches),
+            "metric": "train_patches_per_s", "value": patches / (ms * 1e-3), "unit": "patches/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": patches,
+                       "l2": "per-layer activations (0.2-0.9 GB) and the 0.7 GB of weights exceed the 126 MB L2",
+                       "parallelism": f"dp{world}: one flat fp32 gradient all-reduce (NCCL) per step" if world > 1 else "single GPU",
+                       "optimizer": "torch.optim.AdamW(fused=True), inside the timed step",
+                       "loss": "DiceCE x5 (torch ops on device) + device-side label gather"},
+            "tflops_per_gpu": B * FWD_BWD_GFLOP_PER_PATCH / ms,
+            "loss": loss_value, "peak_mem_gb": round(peak_mem, 2),
+            "e2e": {"value": patches / (e2e_ms * 1e-3), "unit": "patches/s",
+                    "h2d_bytes_per_step": (host_x.numel() + host_y.numel()) * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": int(launches * args.steps),
+            "gpu_launches_per_step": launches,
             "clocks": clocks.summary(),
             "roofline": probe.result(peaks),
+            "sliding_window": sw,
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            per_window, _ = cpu_baseline_sample(threads)
-            line["cpu_baseline"] = {"value": 1.0 / (per_window * NUM_WINDOWS), "unit": "volumes/s", "cores": threads,
-                                    "kind": "port",
-                                    "sample": "1 of 500 windows (oracle CTUNet fp32 forward + Gaussian blend) on the host cores, extrapolated x500"}
+            dt = _oracle_train_step_seconds(threads, 0, 1)
+            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "patches/s", "cores": threads, "kind": "port",
+                                    "sample": "1 patch (batch 1), one step, no warm-up: oracle CTUNet fp32 fwd + 5-head Dice-CE + autograd bwd on the host cores"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -1,0 +1,84 @@
+"""Loss of the CTUNet training step (trainer_CTUNet.py:90-103) with the label handling kept on the device.
+
+`DiceCELoss` restates the subset of monai.losses.DiceCELoss (MONAI 0.7.0) the reference constructs
+(main_CTUNet.py:156-158: to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6):
+    dice = mean over (batch, class) of 1 - (2*sum(p*y) + smooth_nr) / (sum(p^2) + sum(y^2) + smooth_dr)
+    ce   = nn.CrossEntropyLoss()(logits, labels)            total = dice + ce
+`deep_supervision_targets` replaces the two scipy.ndimage.zoom(order=0) host round trips per step
+(trainer_CTUNet.py:93-94) with an index gather on the device that selects exactly the voxels zoom selects.
+`ctunet_loss` is the reference's weighting of the five heads (trainer_CTUNet.py:92-103).
+"""
+from __future__ import annotations
+
+from functools import lru_cache
+from typing import Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class DiceCELoss(nn.Module):
+    def __init__(self, include_background: bool = True, to_onehot_y: bool = False, sigmoid: bool = False,
+                 softmax: bool = False, squared_pred: bool = False, jaccard: bool = False, reduction: str = "mean",
+                 smooth_nr: float = 1e-5, smooth_dr: float = 1e-5, batch: bool = False, lambda_dice: float = 1.0,
+                 lambda_ce: float = 1.0):
+        super().__init__()
+        if not include_background or sigmoid or jaccard or batch or reduction != "mean" or not softmax:
+            raise NotImplementedError("only the configuration the reference builds is restated (main_CTUNet.py:156-158)")
+        self.to_onehot_y, self.squared_pred = to_onehot_y, squared_pred
+        self.smooth_nr, self.smooth_dr = float(smooth_nr), float(smooth_dr)
+        self.lambda_dice, self.lambda_ce = lambda_dice, lambda_ce
+
+    def forward(self, input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        n_cls = input.shape[1]
+        logits = input.float()
+        labels = target.squeeze(1).long() if target.shape[1] == 1 else target.argmax(1)
+        prob = torch.softmax(logits, 1)
+        onehot = F.one_hot(labels, n_cls).movedim(-1, 1).to(prob.dtype) if self.to_onehot_y or target.shape[1] == 1 \
+            else target.float()
+        axes = tuple(range(2, input.dim()))
+        inter = (prob * onehot).sum(axes)
+        if self.squared_pred:
+            den = (prob * prob).sum(axes) + (onehot * onehot).sum(axes)
+        else:
+            den = prob.sum(axes) + onehot.sum(axes)
+        dice = (1.0 - (2.0 * inter + self.smooth_nr) / (den + self.smooth_dr)).mean()
+        ce = F.cross_entropy(logits, labels)
+        return self.lambda_dice * dice + self.lambda_ce * ce
+
+
+@lru_cache(maxsize=None)
+def zoom_indices(n_in: int, n_out: int) -> Tuple[int, ...]:
+    """Source index per output index of scipy.ndimage.zoom(order=0, prefilter=False, grid_mode=False):
+    nearest neighbour of out_idx * (n_in - 1) / (n_out - 1)."""
+    if n_out == 1:
+        return (0,)
+    pos = np.arange(n_out, dtype=np.float64) * (float(n_in - 1) / float(n_out - 1))
+    return tuple(int(v) for v in np.floor(pos + 0.5).astype(np.int64))
+
+
+def zoom_nearest(target: torch.Tensor, zoom: Sequence[float]) -> torch.Tensor:
+    """ndimage.zoom(target, zoom, order=0, prefilter=False) on the device (axes are independent)."""
+    out = target
+    for ax, z in enumerate(zoom):
+        n_in = target.shape[ax]
+        n_out = int(round(n_in * z))
+        if n_out != n_in:
+            idx = torch.as_tensor(zoom_indices(n_in, n_out), device=target.device)
+            out = out.index_select(ax, idx)
+    return out
+
+
+def deep_supervision_targets(target: torch.Tensor):
+    """trainer_CTUNet.py:93-94: labels at 1/2,1/2,1 and 1/4,1/4,1/2 resolution."""
+    return zoom_nearest(target, (1, 1, 0.5, 0.5, 1)), zoom_nearest(target, (1, 1, 0.25, 0.25, 0.5))
+
+
+def ctunet_loss(logits, target: torch.Tensor, loss_func) -> torch.Tensor:
+    """trainer_CTUNet.py:92-103: loss1 = l(full) + 0.5*(l(1/2) + 0.5*l(1/4)); loss = loss1 + 0.5*(l(vit) + l(vit_96))."""
+    t1, t2 = deep_supervision_targets(target)
+    loss1 = loss_func(logits[0][0], target) + 0.5 * (loss_func(logits[0][1], t1) + 0.5 * loss_func(logits[0][2], t2))
+    loss2 = loss_func(logits[1][0], target) + loss_func(logits[1][1], target)
+    return loss1 + 0.5 * loss2
