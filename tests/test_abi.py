@@ -15,7 +15,9 @@ def _declared():
 def test_header_declares_the_hot_path_entry_points():
     names = _declared()
     for must in ("ctu_umma_gemm", "ctu_in_apply", "ctu_in_stats", "ctu_layernorm", "ctu_attention", "ctu_pwa_fuse",
-                 "ctu_blend_accumulate", "ctu_blend_normalize", "ctu_conv_cin1", "ctu_patchify_ln"):
+                 "ctu_blend_accumulate", "ctu_blend_normalize", "ctu_conv_cin1", "ctu_patchify_ln",
+                 "ctu_umma_wgrad", "ctu_in_bwd_stats", "ctu_in_bwd_apply", "ctu_layernorm_bwd", "ctu_attention_bwd",
+                 "ctu_pwa_fuse_bwd", "ctu_gelu_bwd", "ctu_colsum", "ctu_accumulate"):
         assert must in names
 
 
@@ -41,6 +43,28 @@ def test_ctypes_struct_matches_header_field_order():
         if m and "{" not in decl:
             fields += [f.strip().lstrip("*") for f in m.group(3).split(",") if f.strip()]
     assert fields == [f[0] for f in GemmDesc._fields_]
+
+
+def test_wgrad_struct_matches_header_field_order():
+    from hybrid_ctunet_b200.lib import WgradDesc
+    src = open(os.path.join(ROOT, "include", "ctunet_b200.h")).read()
+    start = src.index("typedef struct ctu_wgrad_desc {") + len("typedef struct ctu_wgrad_desc {")
+    body = re.sub(r"/\*.*?\*/", "", src[start:src.index("} ctu_wgrad_desc;")], flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        m = re.match(r"(const\s+)?(void|float|double|int32_t)\s*\*?\s*(.*)", decl.strip())
+        if m and "{" not in decl:
+            fields += [f.strip().lstrip("*") for f in m.group(3).split(",") if f.strip()]
+    assert fields == [f[0] for f in WgradDesc._fields_]
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "hybrid_ctunet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(dirpath, f)
 
 
 def test_no_forbidden_batched_memcpy_symbols():

@@ -76,3 +76,36 @@ def test_full_ctunet_forward_bitwise(ref):
     for u, v in zip(a[0] + a[1], b[0] + b[1]):
         assert u.shape == v.shape
         assert torch.allclose(u, v, rtol=0, atol=1e-4), (u - v).abs().max()
+
+
+def test_gradients_of_reference_modules_equal_oracle_autograd(ref):
+    """The training-step oracle is torch autograd over the restated forward: pin its gradients against the UNMODIFIED
+    reference modules' own backward (train mode, dropout 0) on two blocks and a small training loss."""
+    resnet, _, hyb = ref
+    from oracle import train_oracle as T
+    torch.manual_seed(8)
+    m = hyb.Up_2Fusion_Block(3, 256, 128, 3, (2, 2, 2), "instance").train()
+    inp, sc, sv = torch.randn(1, 256, 3, 3, 6), torch.randn(1, 128, 6, 6, 12), torch.randn(1, 128, 6, 6, 12)
+    tgt = torch.randint(0, 14, (1, 1, 6, 6, 12)).float()
+    head = torch.randn(14, 128, 1, 1, 1)
+    loss = T.dice_ce_loss(torch.nn.functional.conv3d(m(inp, sc, sv), head), tgt)
+    loss.backward()
+    sd = {"blk." + k: v.detach().clone().requires_grad_() for k, v in m.state_dict().items()}
+    loss_o = T.dice_ce_loss(torch.nn.functional.conv3d(O.up_2fusion_block(sd, "blk", inp, sc, sv, 128, (2, 2, 2)), head), tgt)
+    loss_o.backward()
+    assert abs(float(loss) - float(loss_o)) < 1e-6
+    for k, p in m.named_parameters():
+        g = sd["blk." + k].grad
+        if p.grad is None:
+            assert g is None, k
+        else:
+            assert torch.allclose(p.grad, g, rtol=1e-4, atol=1e-7), k
+
+    torch.manual_seed(9)
+    m = resnet.Bottleneck(128, 32).train()
+    x = torch.randn(1, 128, 6, 6, 8)
+    m(x).square().mean().backward()
+    sd = {"blk." + k: v.detach().clone().requires_grad_() for k, v in m.state_dict().items()}
+    O.bottleneck(sd, "blk", x, 1, False).square().mean().backward()
+    for k, p in m.named_parameters():
+        assert torch.allclose(p.grad, sd["blk." + k].grad, rtol=1e-4, atol=1e-8), k
