@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(256) in_bwd_stats_kernel(const __nv_bfloat16* 
   const int rl = threadIdx.x / tpr;
   const int b = blockIdx.y;
   const double inv_n = 1.0 / (double)S;
+  const float inv_slope = 1.f / slope;
   float sg[8], sgx[8], sgr[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sg[j] = sgx[j] = sgr[j] = 0.f;
@@ -91,14 +92,16 @@ __global__ void __launch_bounds__(256) in_bwd_stats_kernel(const __nv_bfloat16* 
       float g[8], o[8], xv[8], rv[8];
       ld8(dout + (base + r) * ldd + cv * 8, g);
       if (act) ld8(out + (base + r) * ldo + cv * 8, o);
-      ld8(x + (base + r) * ldx + cv * 8, xv);
+      if (x != nullptr) ld8(x + (base + r) * ldx + cv * 8, xv);
       if (RES == 2) ld8(res + (base + r) * ldr + cv * 8, rv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float gj = g[j];
         if (act) gj = o[j] > 0.f ? gj : gj * slope;
         sg[j] += gj;
-        sgx[j] += gj * fmaf(xv[j], sc[j], sh[j]);
+        // without a residual the normalised value is recovered from the output: xhat = lrelu^-1(out)
+        const float xh = x != nullptr ? fmaf(xv[j], sc[j], sh[j]) : (o[j] > 0.f ? o[j] : o[j] * inv_slope);
+        sgx[j] += gj * xh;
         if (RES == 2) sgr[j] += gj * fmaf(rv[j], rsc[j], rsh[j]);
       }
     }
@@ -161,17 +164,18 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __nv_bfloat16* 
     mgr[j] = RES == 2 ? (float)(sp[2] * inv_n) : 0.f;
   }
   const long long base = (long long)b * S;
+  const float inv_slope = 1.f / slope;
   for (long long r = (long long)blockIdx.x * rpb + rl; r < S; r += (long long)gridDim.x * rpb) {
     float g[8], o[8], xv[8], rv[8], ox[8], orr[8];
     ld8(dout + (base + r) * ldd + cv * 8, g);
     if (act) ld8(out + (base + r) * ldo + cv * 8, o);
-    ld8(x + (base + r) * ldx + cv * 8, xv);
+    if (x != nullptr) ld8(x + (base + r) * ldx + cv * 8, xv);
     if (RES == 2) ld8(res + (base + r) * ldr + cv * 8, rv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float gj = g[j];
       if (act) gj = o[j] > 0.f ? gj : gj * slope;
-      const float xh = fmaf(xv[j], sc[j], sh[j]);
+      const float xh = x != nullptr ? fmaf(xv[j], sc[j], sh[j]) : (o[j] > 0.f ? o[j] : o[j] * inv_slope);
       ox[j] = sc[j] * (gj - mg[j] - xh * mgx[j]);
       if (RES == 1) orr[j] = gj;
       if (RES == 2) {
@@ -185,10 +189,12 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __nv_bfloat16* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm backward: one warp per row, rows strided over a persistent grid so that the per-channel dgamma /
-// dbeta partial sums live in registers and are flushed with one atomic per (warp, channel).
-//   dx = rstd * (gamma*dy - mean(gamma*dy) - xhat * mean(gamma*dy*xhat)) [+ dx_in]
-template <int VPL, typename TIN>
+// LayerNorm backward.  dx = rstd * (gamma*dy - mean(gamma*dy) - xhat * mean(gamma*dy*xhat)) [+ dx_in].
+// A row is handled by LPR lanes (8 channels per lane and vector, VPL vectors per lane): LPR = C/8 for C <= 256 so a
+// warp works on several rows at once, a whole warp with VPL = 2..4 vectors for wider rows.  Rows are strided over a
+// persistent grid; the per-channel dgamma / dbeta partial sums live in registers, are combined per block in shared
+// memory and flushed with ONE global atomic per (block, channel).
+template <int LPR, int VPL, typename TIN>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TIN* __restrict__ x, long long ldx,
                                                             const float* __restrict__ gamma,
                                                             const __nv_bfloat16* __restrict__ dy, long long ldd,
@@ -197,24 +203,32 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TIN* __restric
                                                             __nv_bfloat16* __restrict__ dx_bf, long long ld_b,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                             long long M, int C, float eps) {
-  const int lane = threadIdx.x & 31;
+  extern __shared__ float ln_red[];  // [2][C]
+  constexpr int RPB = 256 / LPR;     // rows per block iteration
+  const int sub = threadIdx.x % LPR;
+  const int rl = threadIdx.x / LPR;
   const int nvec = C / 8;
+  for (int i = threadIdx.x; i < 2 * C; i += 256) ln_red[i] = 0.f;
   float dg[VPL][8], db[VPL][8], gm[VPL][8];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int vi = lane + 32 * i;
+    const int vi = sub + LPR * i;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; gm[i][j] = 0.f; }
     if (vi < nvec) ld8f(gamma + vi * 8, gm[i]);
   }
   const float invC = 1.f / (float)C;
-  for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * 8) {
+  // block-uniform trip count: every lane takes part in the shuffles, out-of-range rows are masked
+  const long long iters = (M + (long long)gridDim.x * RPB - 1) / ((long long)gridDim.x * RPB);
+  for (long long it = 0; it < iters; ++it) {
+    const long long row = (it * gridDim.x + blockIdx.x) * RPB + rl;
+    const bool rok = row < M;
     float v[VPL][8], d[VPL][8];
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int vi = lane + 32 * i;
-      if (vi < nvec) {
+      const int vi = sub + LPR * i;
+      if (rok && vi < nvec) {
         if constexpr (sizeof(TIN) == 2) ld8(reinterpret_cast<const __nv_bfloat16*>(x) + row * ldx + vi * 8, v[i]);
         else ld8f(reinterpret_cast<const float*>(x) + row * ldx + vi * 8, v[i]);
         ld8(dy + row * ldd + vi * 8, d[i]);
@@ -226,23 +240,23 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TIN* __restric
       }
     }
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int o = LPR / 2; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float mean = sum * invC;
     float sq = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      if (lane + 32 * i < nvec) {
+      if (sub + LPR * i < nvec) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float t = v[i][j] - mean; sq += t * t; }
       }
     }
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    for (int o = LPR / 2; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     const float rstd = rsqrtf(sq * invC + eps);
     float m1 = 0.f, m2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      if (lane + 32 * i < nvec) {
+      if (rok && sub + LPR * i < nvec) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xh = (v[i][j] - mean) * rstd;
@@ -256,15 +270,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TIN* __restric
       }
     }
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
+    for (int o = LPR / 2; o >= 1; o >>= 1) {
       m1 += __shfl_xor_sync(0xffffffffu, m1, o);
       m2 += __shfl_xor_sync(0xffffffffu, m2, o);
     }
     m1 *= invC; m2 *= invC;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int vi = lane + 32 * i;
-      if (vi < nvec) {
+      const int vi = sub + LPR * i;
+      if (rok && vi < nvec) {
         float o8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o8[j] = rstd * (gm[i][j] * d[i][j] - m1 - v[i][j] * m2);
@@ -280,16 +294,22 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TIN* __restric
       }
     }
   }
+  __syncthreads();  // ln_red zero-fill visible
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int vi = lane + 32 * i;
+    const int vi = sub + LPR * i;
     if (vi < nvec) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(dgamma + vi * 8 + j, dg[i][j]);
-        atomicAdd(dbeta + vi * 8 + j, db[i][j]);
+        atomicAdd(&ln_red[vi * 8 + j], dg[i][j]);
+        atomicAdd(&ln_red[C + vi * 8 + j], db[i][j]);
       }
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) {
+    atomicAdd(dgamma + i, ln_red[i]);
+    atomicAdd(dbeta + i, ln_red[C + i]);
   }
 }
 
@@ -674,8 +694,9 @@ extern "C" int ctu_in_bwd_stats(const void* dout, int ldd, const void* out, int 
                                 const double* xstats, int xs_ld, const void* res, int ldr, const double* rstats,
                                 int rs_ld, int B, long long S, int C, float eps, int act, float slope, double* sums,
                                 void* stream) {
-  if (!dout || !x || !xstats || !sums || (act && !out) || C % 8 || C > 2048 || (2048 % C)) return CTU_E_BADARG;
-  if (ldd % 8 || ldx % 8 || (act && ldo % 8) || (rstats && (!res || ldr % 8))) return CTU_E_BADARG;
+  if (!dout || !xstats || !sums || (act && !out) || C % 8 || C > 2048 || (2048 % C)) return CTU_E_BADARG;
+  if (!x && (!act || res)) return CTU_E_BADARG;  /* xhat from the output needs the invertible activation, no residual */
+  if (ldd % 8 || (x && ldx % 8) || (act && ldo % 8) || (rstats && (!res || ldr % 8))) return CTU_E_BADARG;
   dim3 grid;
   in_grid(S, C, B, 16, grid);
   cudaStream_t st = (cudaStream_t)stream;
@@ -693,8 +714,9 @@ extern "C" int ctu_in_bwd_apply(const void* dout, int ldd, const void* out, int 
                                 const double* xstats, int xs_ld, const void* res, int ldr, const double* rstats,
                                 int rs_ld, int res_mode, int B, long long S, int C, float eps, int act, float slope,
                                 const double* sums, void* dx, int lddx, void* dres, int lddr, void* stream) {
-  if (!dout || !x || !xstats || !sums || !dx || (act && !out) || C % 8 || C > 2048 || (2048 % C)) return CTU_E_BADARG;
-  if (ldd % 8 || ldx % 8 || lddx % 8 || (act && ldo % 8)) return CTU_E_BADARG;
+  if (!dout || !xstats || !sums || !dx || (act && !out) || C % 8 || C > 2048 || (2048 % C)) return CTU_E_BADARG;
+  if (!x && (!act || res_mode != 0)) return CTU_E_BADARG;
+  if (ldd % 8 || (x && ldx % 8) || lddx % 8 || (act && ldo % 8)) return CTU_E_BADARG;
   if (res_mode < 0 || res_mode > 2 || (res_mode && (!dres || lddr % 8)) || (res_mode == 2 && (!res || !rstats || ldr % 8)))
     return CTU_E_BADARG;
   dim3 grid;
@@ -716,17 +738,22 @@ template <typename TIN>
 static int launch_ln_bwd(const void* x, long long ldx, const float* gamma, const void* dy, long long ldd, const void* dx_in,
                          int dxin_f32, long long ld_in, float* dx_f32, long long ld_f, void* dx_bf, long long ld_b,
                          float* dgamma, float* dbeta, long long M, int C, float eps, cudaStream_t st) {
-  const int vpl = (C / 8 + 31) / 32;
-  long long blocks = (M + 7) / 8;
-  const long long cap = (long long)bw_num_sms() * 4;
-  if (blocks > cap) blocks = cap;
-#define CTU_LNB(V)                                                                                                     \
-  layernorm_bwd_kernel<V, TIN><<<(unsigned)blocks, 256, 0, st>>>((const TIN*)x, ldx, gamma, (const bf16*)dy, ldd, dx_in, \
-                                                                 dxin_f32, ld_in, dx_f32, ld_f, (bf16*)dx_bf, ld_b,     \
-                                                                 dgamma, dbeta, M, C, eps)
-  if (vpl <= 1) CTU_LNB(1);
-  else if (vpl <= 2) CTU_LNB(2);
-  else if (vpl <= 4) CTU_LNB(4);
+  const int nvec = C / 8;
+  const size_t smem = 2 * (size_t)C * sizeof(float);
+#define CTU_LNB(L, V)                                                                                                  \
+  do {                                                                                                                 \
+    long long blocks = (M + (256 / L) - 1) / (256 / L);                                                                \
+    const long long cap = (long long)bw_num_sms() * 6;                                                                 \
+    if (blocks > cap) blocks = cap;                                                                                    \
+    layernorm_bwd_kernel<L, V, TIN><<<(unsigned)blocks, 256, smem, st>>>((const TIN*)x, ldx, gamma, (const bf16*)dy, ldd, \
+                                                                         dx_in, dxin_f32, ld_in, dx_f32, ld_f,         \
+                                                                         (bf16*)dx_bf, ld_b, dgamma, dbeta, M, C, eps); \
+  } while (0)
+  if (nvec <= 8) CTU_LNB(8, 1);
+  else if (nvec <= 16) CTU_LNB(16, 1);
+  else if (nvec <= 32) CTU_LNB(32, 1);
+  else if (nvec <= 64) CTU_LNB(32, 2);
+  else if (nvec <= 128) CTU_LNB(32, 4);
   else return CTU_E_UNSUPPORTED;
 #undef CTU_LNB
   count_launch();

@@ -467,7 +467,8 @@ class Engine:
                 B, C = x.shape[0], x.shape[-1]
                 dx = self._empty(*x.shape)
                 dres = self._empty(*res.shape) if res is not None else None
-                ops.in_backward(g, out, x, st, dx, res=res, rstats=rstats, dres=dres, sums=self.bsums.take(B, C, 4))
+                ops.in_backward(g, out, x if res is not None else None, st, dx, res=res, rstats=rstats, dres=dres,
+                                sums=self.bsums.take(B, C, 4))
                 self._acc(x, dx)
                 if res is not None:
                     self._acc(res, dres)

@@ -298,20 +298,22 @@ def _bsc(x: torch.Tensor):
 
 def in_backward(dout, out, x, xstats, dx, *, res=None, rstats=None, dres=None, sums=None, act: bool = True):
     """Backward of in_apply.  dout/out/x(/res): bf16 [B, ..., C]; writes dx (and dres when the forward had a residual:
-    the raw gradient g for an identity residual, the InstanceNorm backward for a normalised one)."""
+    the raw gradient g for an identity residual, the InstanceNorm backward for a normalised one).  x may be None when
+    the forward had no residual (xhat is recovered from `out`)."""
     lib = _lib.require_device()
-    B, S, C_ = _bsc(x)
+    B, S, C_ = _bsc(out)
     if sums is None:
-        sums = torch.zeros(B, C_, 4, dtype=torch.float64, device=x.device)
+        sums = torch.zeros(B, C_, 4, dtype=torch.float64, device=out.device)
     res_mode = 0 if dres is None else (2 if rstats is not None else 1)
     r2 = res if res_mode == 2 else None
-    check(lib.ctu_in_bwd_stats(dout.data_ptr(), int(dout.stride(-2)), out.data_ptr(), int(out.stride(-2)), x.data_ptr(),
-                               int(x.stride(-2)), xstats.data_ptr(), int(xstats.shape[-2]), _ptr(r2),
+    ldx = 0 if x is None else int(x.stride(-2))
+    check(lib.ctu_in_bwd_stats(dout.data_ptr(), int(dout.stride(-2)), out.data_ptr(), int(out.stride(-2)), _ptr(x),
+                               ldx, xstats.data_ptr(), int(xstats.shape[-2]), _ptr(r2),
                                0 if r2 is None else int(r2.stride(-2)), _ptr(rstats) if res_mode == 2 else None,
                                0 if res_mode != 2 else int(rstats.shape[-2]), B, S, C_, IN_EPS, 1 if act else 0,
                                LRELU_SLOPE, sums.data_ptr(), _stream()), "ctu_in_bwd_stats")
-    check(lib.ctu_in_bwd_apply(dout.data_ptr(), int(dout.stride(-2)), out.data_ptr(), int(out.stride(-2)), x.data_ptr(),
-                               int(x.stride(-2)), xstats.data_ptr(), int(xstats.shape[-2]), _ptr(r2),
+    check(lib.ctu_in_bwd_apply(dout.data_ptr(), int(dout.stride(-2)), out.data_ptr(), int(out.stride(-2)), _ptr(x),
+                               ldx, xstats.data_ptr(), int(xstats.shape[-2]), _ptr(r2),
                                0 if r2 is None else int(r2.stride(-2)), _ptr(rstats) if res_mode == 2 else None,
                                0 if res_mode != 2 else int(rstats.shape[-2]), res_mode, B, S, C_, IN_EPS,
                                1 if act else 0, LRELU_SLOPE, sums.data_ptr(), dx.data_ptr(), int(dx.stride(-2)),

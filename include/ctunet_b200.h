@@ -153,7 +153,9 @@ int ctu_umma_wgrad(const ctu_wgrad_desc* desc, void* stream);
 /* Backward of ctu_in_apply: out = act(IN(x) [+ res | + IN(res)]).  With g = dout * act'(out):
  *   dx = rstd_x * (g - mean(g) - xhat * mean(g*xhat)); dres = g (res_mode 1) or the same formula with the
  *   residual's statistics (res_mode 2).  ctu_in_bwd_stats accumulates sums[b][c] = (sum g, sum g*xhat, sum g*rhat, -)
- *   as fp64 [B][C][4] (zeroed by the caller; pass rstats == NULL unless res_mode == 2); ctu_in_bwd_apply consumes it. */
+ *   as fp64 [B][C][4] (zeroed by the caller; pass rstats == NULL unless res_mode == 2); ctu_in_bwd_apply consumes it.
+ *   With act != 0 and no residual, x may be NULL: xhat is then recovered from the output, xhat = LeakyReLU^-1(out),
+ *   which saves one tensor read per pass. */
 int ctu_in_bwd_stats(const void* dout, int ldd, const void* out, int ldo, const void* x, int ldx, const double* xstats,
                      int xs_ld, const void* res, int ldr, const double* rstats, int rs_ld, int B, long long S, int C,
                      float eps, int act, float slope, double* sums, void* stream);
