@@ -580,7 +580,12 @@ extern "C" int ctu_umma_gemm(const ctu_gemm_desc* d, void* stream_) {
       // 3x3x3 convolutions with 64 output channels: three CTAs per SM (measured 1.04 vs 1.10 ms at 96^3 x 4)
       if (variant == 3 || (variant == 0 && p.num_kb >= 27)) return launch_gemm<64, 2, 1, 3>(tmA, tmB, tmC, p, stream);
       return launch_gemm<64, 3, 1, 2>(tmA, tmB, tmC, p, stream);
-    case 128: return launch_gemm<128, 2, 1, 2>(tmA, tmB, tmC, p, stream);
+    case 128:
+      // few tiles with a long K loop (ViT GEMMs: 42-168 tiles of 12-48 K blocks): one CTA per SM with a deep ring hides
+      // the L2 latency that two 2-stage CTAs cannot when most SMs hold a single tile
+      if (variant == 5 || (variant == 0 && p.num_kb >= 8 && p.total_tiles <= 2 * sm_count()))
+        return launch_gemm<128, 5, 1, 1>(tmA, tmB, tmC, p, stream);
+      return launch_gemm<128, 2, 1, 2>(tmA, tmB, tmC, p, stream);
     case 256: return launch_gemm<256, 3, 1, 1>(tmA, tmB, tmC, p, stream);
     default: return CTU_E_UNSUPPORTED;
   }

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "../../include/ctunet_b200.h"
 #include "host_util.h"
+#include <stdlib.h>
 
 namespace ctu {
 
@@ -59,15 +60,18 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 
 struct WgItem {
-  int mg, nt, v0, v1;
+  int m0, m1, nt, v0, v1;  // row tiles [m0, m1), output-channel block, voxel tiles [v0, v1)
 };
 
 __device__ __forceinline__ WgItem wg_decode(const WgradParams& p, int item) {
   WgItem w;
   w.nt = item % p.NT;
   int t = item / p.NT;
-  w.mg = t % p.MG;
+  const int mg = t % p.MG;
   const int s = t / p.MG;
+  // row tiles are spread evenly over the MG groups (at most J per group)
+  w.m0 = (p.MT * mg) / p.MG;
+  w.m1 = (p.MT * (mg + 1)) / p.MG;
   w.v0 = (int)(((long long)p.vox_tiles * s) / p.splits);
   w.v1 = (int)(((long long)p.vox_tiles * (s + 1)) / p.splits);
   return w;
@@ -138,9 +142,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_wgrad_kernel(const __gr
               tma_load_5d(smem_u32(smem_b + s * B_STAGE_BYTES + sl * WG_SLAB_BYTES), &tmY, full, n0 + sl * 64, x1, x2, x3, t4);
             ++ib;
           }
-          for (int j = 0; j < J; ++j) {
-            const int mt = w.mg * J + j;
-            if (mt >= p.MT) break;
+          for (int mt = w.m0; mt < w.m1; ++mt) {
             const int s = ia % SA;
             mbar_wait(smem_u32(&empty_a[s]), ((ia / SA) & 1) ^ 1);
             const uint32_t full = smem_u32(&full_a[s]);
@@ -181,9 +183,8 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_wgrad_kernel(const __gr
           mbar_wait(smem_u32(&full_b[sb]), (ib / SB) & 1);
           tc_fence_after();
           const uint64_t db = umma_desc_mn_sw128(smem_u32(smem_b + sb * B_STAGE_BYTES), WG_SLAB_BYTES);
-          for (int j = 0; j < J; ++j) {
-            const int mt = w.mg * J + j;
-            if (mt >= p.MT) break;
+          for (int mt = w.m0; mt < w.m1; ++mt) {
+            const int j = mt - w.m0;
             const int sa = ia % SA;
             mbar_wait(smem_u32(&full_a[sa]), (ia / SA) & 1);
             tc_fence_after();
@@ -214,9 +215,8 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_wgrad_kernel(const __gr
       mbar_wait(smem_u32(bar_tfull), li & 1);
       tc_fence_after();
       if (w.v1 > w.v0) {
-        for (int j = 0; j < J; ++j) {
-          const int mt = w.mg * J + j;
-          if (mt >= p.MT) break;
+        for (int mt = w.m0; mt < w.m1; ++mt) {
+          const int j = mt - w.m0;
           const int slab = 2 * mt + (r >> 6);
           const bool row_ok = slab < p.nslabs;
           float* drow = p.dw + ((long long)slab * 64 + (r & 63)) * p.ldw + n0;
@@ -257,7 +257,7 @@ static int wg_sm_count() {
 }
 
 template <int BN, int J, int SA, int SB, int CTAS_PER_SM>
-static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmY, WgradParams p, cudaStream_t stream) {
+static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmY, WgradParams p, int per_slot, cudaStream_t stream) {
   constexpr int smem = 1024 + SA * WG_A_STAGE_BYTES + SB * (BN / 64) * WG_SLAB_BYTES + (2 * SA + 2 * SB + 2) * 8 + 16;
   static_assert(CTAS_PER_SM * (smem + 1024) <= 228 * 1024, "shared memory budget");
   static_assert(CTAS_PER_SM * J * BN <= 512, "TMEM budget");
@@ -271,8 +271,12 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmY, WgradPar
   p.MG = (p.MT + J - 1) / J;
   const int slots = wg_sm_count() * CTAS_PER_SM;
   const int base = p.MG * p.NT;
-  // split the voxel axis so that every CTA slot gets about two work items
-  int splits = (2 * slots + base - 1) / base;
+  // split the voxel axis so that every CTA slot gets `per_slot` work items: more, shorter items balance the SMs
+  // better; fewer, longer items mean fewer fp32 reductions in the epilogue (measured per shape class, see
+  // profiles/r01_wgrad_sweep.txt)
+  static const int forced = [] { const char* e = getenv("CTU_WGRAD_ITEMS_PER_SLOT"); return e ? atoi(e) : 0; }();
+  if (forced > 0) per_slot = forced;
+  int splits = (per_slot * slots + base - 1) / base;
   if (splits > p.vox_tiles) splits = p.vox_tiles;
   if (splits < 1) splits = 1;
   p.splits = splits;
@@ -340,10 +344,24 @@ extern "C" int ctu_umma_wgrad(const ctu_wgrad_desc* d, void* stream_) {
   p.dw = d->dw; p.ldw = d->ldw; p.n = d->n;
   p.MG = 0; p.splits = 1; p.total_items = 0;
 
+  // Launch shapes (CUDA-event sweep on B200, profiles/r01_wgrad_sweep.txt): several small CTAs per SM beat one CTA
+  // with a deep ring — like the forward kernel, one MMA-issuing thread cannot keep the tensor pipe busy with
+  // N <= 128 instructions — and large problems want 6-8 work items per CTA slot.
+  static const int variant = [] { const char* e = getenv("CTU_WGRAD_VARIANT"); return e ? atoi(e) : -1; }();
+  const bool conv = d->k1 == 3;
   switch (d->block_n) {
-    case 64: return launch_wgrad<64, 4, 2, 2, 2>(tmX, tmY, p, stream);
-    case 128: return launch_wgrad<128, 4, 3, 2, 1>(tmX, tmY, p, stream);
-    case 256: return launch_wgrad<256, 2, 2, 2, 1>(tmX, tmY, p, stream);
+    case 64:
+      if (variant == 0 || (variant < 0 && p.vox_tiles < 8000)) return launch_wgrad<64, 4, 2, 2, 2>(tmX, tmY, p, 1, stream);
+      if (variant == 1) return launch_wgrad<64, 8, 3, 2, 1>(tmX, tmY, p, 2, stream);
+      return launch_wgrad<64, 2, 1, 1, 4>(tmX, tmY, p, 8, stream);
+    case 128:
+      if (variant == 0) return launch_wgrad<128, 4, 3, 2, 1>(tmX, tmY, p, 2, stream);
+      if (variant == 1 || (variant < 0 && (p.vox_tiles < 2000 || (!conv && p.MT * p.NT < 3))))
+        return launch_wgrad<128, 2, 2, 1, 2>(tmX, tmY, p, 1, stream);
+      return launch_wgrad<128, 1, 1, 1, 3>(tmX, tmY, p, conv ? 6 : 2, stream);
+    case 256:
+      if (variant == 1) return launch_wgrad<256, 1, 1, 1, 2>(tmX, tmY, p, 2, stream);
+      return launch_wgrad<256, 2, 2, 2, 1>(tmX, tmY, p, conv && p.vox_tiles >= 400 ? 4 : (conv ? 1 : 2), stream);
     default: return CTU_E_UNSUPPORTED;
   }
 }

@@ -51,6 +51,11 @@ mk_lin("pwa256_qkv", T2, 256, 768)
 mk_lin("ffn256_up_gelu", T2, 256, 1024, act=1, bias=True)
 mk_lin("vit_qkv", B * 432, 768, 2304)
 mk_lin("vit_ffn_up", B * 432, 768, 3072, act=1, bias=True)
+mk_lin("vit2_qkv", 864, 768, 2304)
+mk_lin("vit2_ffn_up", 864, 768, 3072, bias=True)
+mk_lin("vit2_ffn_down", 864, 3072, 768, bias=True)
+mk_lin("vit2_out", 864, 768, 768, bias=True)
+mk_lin("vit2_dgrad_qkv", 864, 2304, 768)
 res = {}
 for name, fn, flops, bytes_ in shapes:
     fn(); torch.cuda.synchronize()
