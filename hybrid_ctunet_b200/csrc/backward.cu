@@ -537,32 +537,40 @@ __global__ void __launch_bounds__(256) subsample_bwd_kernel(const __nv_bfloat16*
 
 // ------------------------------------------------------------------------------------------------
 // im2col of a single-channel fp32 volume into channels-last bf16 rows [B][Xo][Yo][Zo][kpad] (tap-major columns,
-// taps..kpad-1 zero): lets the weight gradient of the C_in = 1 convolutions (ResNet stem, vit_encoder0) run on the
-// tensor-core wgrad kernel.  One warp per output voxel.
+// taps..kpad-1 zero): lets the C_in = 1 convolutions (ResNet stem forward, and the weight gradients of the stem and of
+// vit_encoder0) run on the tensor-core kernels.
 __global__ void __launch_bounds__(256) im2col_cin1_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out,
                                                           int B, int X, int Y, int Z, int Xo, int Yo, int Zo, int kx,
                                                           int ky, int kz, int sx, int sy, int sz, int px, int py, int pz,
                                                           int kpad) {
-  const int lane = threadIdx.x & 31;
-  const long long nvox = (long long)B * Xo * Yo * Zo;
+  // one thread per (output voxel, group of 8 taps): 8 gathered pixels -> one 16-byte store
+  const int gpv = kpad / 8;
+  const long long total = (long long)B * Xo * Yo * Zo * gpv;
   const int taps = kx * ky * kz;
-  for (long long v = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); v < nvox; v += (long long)gridDim.x * 8) {
-    long long t = v;
-    const int zo = (int)(t % Zo); t /= Zo;
-    const int yo = (int)(t % Yo); t /= Yo;
-    const int xo = (int)(t % Xo);
-    const int b = (int)(t / Xo);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long v = i / gpv;
+    const int grp = (int)(i - v * gpv);
+    const long long vox = v;
+    const int zo = (int)(v % Zo); v /= Zo;
+    const int yo = (int)(v % Yo); v /= Yo;
+    const int xo = (int)(v % Xo);
+    const int b = (int)(v / Xo);
     const float* ib = img + (long long)b * X * Y * Z;
-    __nv_bfloat16* op = out + v * kpad;
-    for (int k = lane; k < kpad; k += 32) {
-      float val = 0.f;
-      if (k < taps) {
-        const int fz = k % kz, fy = (k / kz) % ky, fx = k / (kz * ky);
-        const int x = xo * sx - px + fx, y = yo * sy - py + fy, z = zo * sz - pz + fz;
-        if (x >= 0 && x < X && y >= 0 && y < Y && z >= 0 && z < Z) val = ib[((long long)x * Y + y) * Z + z];
+    const int x0 = xo * sx - px, y0 = yo * sy - py, z0 = zo * sz - pz;
+    int k = grp * 8;
+    int fz = k % kz, fy = (k / kz) % ky, fx = k / (kz * ky);
+    float val[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = 0.f;
+      if (k + e < taps) {
+        const int x = x0 + fx, y = y0 + fy, z = z0 + fz;
+        if (x >= 0 && x < X && y >= 0 && y < Y && z >= 0 && z < Z) t = __ldg(ib + ((long long)x * Y + y) * Z + z);
       }
-      op[k] = __float2bfloat16(val);
+      val[e] = t;
+      if (++fz == kz) { fz = 0; if (++fy == ky) { fy = 0; ++fx; } }
     }
+    st8(out + vox * kpad + grp * 8, val);
   }
 }
 
@@ -850,7 +858,7 @@ extern "C" int ctu_im2col_cin1(const float* img, void* out, int B, int X, int Y,
   if (!img || !out || kpad % 8 || kpad < kx * ky * kz) return CTU_E_BADARG;
   const int Xo = (X + 2 * px - kx) / sx + 1, Yo = (Y + 2 * py - ky) / sy + 1, Zo = (Z + 2 * pz - kz) / sz + 1;
   const long long nvox = (long long)B * Xo * Yo * Zo;
-  im2col_cin1_kernel<<<bw_grid(nvox, 8), 256, 0, (cudaStream_t)stream>>>(img, (bf16*)out, B, X, Y, Z, Xo, Yo, Zo, kx, ky, kz,
+  im2col_cin1_kernel<<<bw_grid(nvox * (kpad / 8), 256), 256, 0, (cudaStream_t)stream>>>(img, (bf16*)out, B, X, Y, Z, Xo, Yo, Zo, kx, ky, kz,
                                                                          sx, sy, sz, px, py, pz, kpad);
   count_launch();
   return (int)cudaGetLastError();

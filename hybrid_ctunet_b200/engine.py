@@ -70,6 +70,8 @@ class WeightCache:
             return self.convt(name)
         if kind == "ps":
             return self.pixel_shuffle(name, extra)
+        if kind == "cin1":
+            return self.conv_cin1_tc(name)
         raise KeyError(kind)
 
     def get_t(self, kind: str, name: str, extra=None) -> PackedWeight:
@@ -174,6 +176,17 @@ class WeightCache:
     def conv_cin1(self, name: str) -> torch.Tensor:
         return self._get("d1:" + name, [name + ".weight"],
                          lambda w: w.reshape(w.shape[0], -1).t().contiguous().float())
+
+    # -- the same weights as a [Cout, taps padded to 64n] bf16 matrix for the tensor-core path over an im2col operand
+    def conv_cin1_tc(self, name: str) -> PackedWeight:
+        def build(w):
+            co = w.shape[0]
+            taps = w[0].numel()
+            kpad = -(-taps // 64) * 64
+            wp = torch.zeros(co, kpad, device=w.device, dtype=w.dtype)
+            wp[:, :taps] = w.reshape(co, taps)
+            return ops.pack_matrix(wp)
+        return self._get("d1tc:" + name, [name + ".weight"], build)
 
     def rel_bias(self, name: str, w: int = 6) -> torch.Tensor:
         def build(emb):
@@ -698,10 +711,14 @@ class Engine:
         """resnet.py:213-230 (no max pool): stem k7 s(2,2,1) -> IN -> lrelu -> 4 stages; returns 4 feature maps."""
         B, _, X, Y, Z = x_in.shape
         s0 = DS_STRIDE[0]
-        x = self._empty(B, (X + 6 - 7) // s0[0] + 1, (Y + 6 - 7) // s0[1] + 1, (Z + 6 - 7) // s0[2] + 1, 64)
-        self.conv_cin1(x_in, pre + "conv1.conv", x, k=(7, 7, 7), s=s0, p=(3, 3, 3))
+        Xo, Yo, Zo = (X + 6 - 7) // s0[0] + 1, (Y + 6 - 7) // s0[1] + 1, (Z + 6 - 7) // s0[2] + 1
+        # stem k7 (343 taps) on the tensor cores: single-channel im2col (taps zero-padded to 384 columns) + GEMM with the
+        # InstanceNorm statistics in the epilogue; the column matrix is kept for the weight gradient in training
+        col = self._empty(B, Xo, Yo, Zo, 384)
+        ops.im2col_cin1(x_in, col, k=(7, 7, 7), s=s0, p=(3, 3, 3))
         st = self.stats.take(B, 64)
-        ops.in_stats(x, st)
+        x = self.gemm(col, "cin1", pre + "conv1.conv", self._empty(B, Xo, Yo, Zo, 64), dims=(Zo, Yo, Xo, B), stats=st,
+                      a_needs_grad=False)
         x = self.in_apply(x, st)
         feats = []
         strides = [(1, 1, 1), DS_STRIDE[1], DS_STRIDE[2], DS_STRIDE[3]]

@@ -1,7 +1,9 @@
 """Loss of the CTUNet training step (trainer_CTUNet.py:90-103) with the label handling kept on the device.
 
 `DiceCELoss` restates the subset of monai.losses.DiceCELoss (MONAI 0.7.0) the reference constructs
-(main_CTUNet.py:156-158: to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6):
+(main_CTUNet.py:156-158: to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6); on CUDA
+tensors it runs on the fused kernels ctu_dice_ce_fwd / ctu_dice_ce_bwd (csrc/loss.cu), the torch expression below
+is the definition used for CPU tensors (tests) and for configurations the reference never builds:
     dice = mean over (batch, class) of 1 - (2*sum(p*y) + smooth_nr) / (sum(p^2) + sum(y^2) + smooth_dr)
     ce   = nn.CrossEntropyLoss()(logits, labels)            total = dice + ce
 `deep_supervision_targets` replaces the two scipy.ndimage.zoom(order=0) host round trips per step
@@ -19,6 +21,50 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+_FUSED_CLASSES = (2, 3, 4, 14)
+
+
+class _DiceCEFused(torch.autograd.Function):
+    """Dice-CE on the fused CUDA kernels (ctu_dice_ce_fwd / ctu_dice_ce_bwd): two passes over the logits in total."""
+
+    @staticmethod
+    def forward(ctx, logits, target, smooth_nr, smooth_dr, lambda_dice, lambda_ce):
+        from . import lib as _lib
+        lib = _lib.require_device()
+        logits = logits.float().contiguous()
+        target = target.float().contiguous()
+        B, C = logits.shape[:2]
+        S = logits.numel() // (B * C)
+        if target.numel() != B * S:
+            raise ValueError(f"ground truth has different shape ({tuple(target.shape)}) from input ({tuple(logits.shape)})")
+        sums = torch.zeros(B * C * 3 + 1, dtype=torch.float64, device=logits.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.ctu_dice_ce_fwd(logits.data_ptr(), target.data_ptr(), B, C, S, sums.data_ptr(), stream), "ctu_dice_ce_fwd")
+        s = sums[:B * C * 3].view(B, C, 3)
+        inter, den = s[..., 0], s[..., 1] + s[..., 2] + smooth_dr
+        dice = (1.0 - (2.0 * inter + smooth_nr) / den).mean()
+        ce = sums[-1] / float(B * S)
+        ctx.save_for_backward(logits, target, inter, den)
+        ctx.cfg = (B, C, S, smooth_nr, lambda_dice, lambda_ce)
+        return (lambda_dice * dice + lambda_ce * ce).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import lib as _lib
+        lib = _lib.require_device()
+        logits, target, inter, den = ctx.saved_tensors
+        B, C, S, smooth_nr, lambda_dice, lambda_ce = ctx.cfg
+        scale = g.double() * (lambda_dice / float(B * C))
+        coef = torch.stack((scale * (-2.0 / den), scale * (2.0 * (2.0 * inter + smooth_nr) / (den * den))), dim=-1)
+        coef = coef.float().contiguous()
+        ce_scale = (g.double() * (lambda_ce / float(B * S))).float().reshape(1).contiguous()
+        dlogits = torch.empty_like(logits)
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.ctu_dice_ce_bwd(logits.data_ptr(), target.data_ptr(), B, C, S, coef.data_ptr(), ce_scale.data_ptr(),
+                                       dlogits.data_ptr(), stream), "ctu_dice_ce_bwd")
+        return dlogits, None, None, None, None, None
+
+
 class DiceCELoss(nn.Module):
     def __init__(self, include_background: bool = True, to_onehot_y: bool = False, sigmoid: bool = False,
                  softmax: bool = False, squared_pred: bool = False, jaccard: bool = False, reduction: str = "mean",
@@ -33,6 +79,9 @@ class DiceCELoss(nn.Module):
 
     def forward(self, input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         n_cls = input.shape[1]
+        if (input.is_cuda and self.squared_pred and target.shape[1] == 1 and n_cls in _FUSED_CLASSES and input.dim() == 5):
+            # the configuration the reference trains with: fused kernels (no eager fallback on the GPU)
+            return _DiceCEFused.apply(input, target, self.smooth_nr, self.smooth_dr, self.lambda_dice, self.lambda_ce)
         logits = input.float()
         labels = target.squeeze(1).long() if target.shape[1] == 1 else target.argmax(1)
         prob = torch.softmax(logits, 1)

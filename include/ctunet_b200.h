@@ -219,6 +219,18 @@ int ctu_attention_bwd(const void* qkv, int ld_qkv, int C, int dim_head, const vo
                       const float* delta, const float* biasT, void* dqkv, int ld_dqkv, float* dq_f32, void* ds_out, int n,
                       int windows, int mode, int batch, int X, int Y, int Z, int w, void* stream);
 
+/* Fused Dice-CE loss (trainer_CTUNet.py:92-103 calls monai.losses.DiceCELoss(to_onehot_y, softmax, squared_pred) on
+ * five heads).  logits: fp32 NCDHW [B][C][S]; target: fp32 labels [B][S] (class index stored as float, as the
+ * reference's loaders yield them); C in {2,3,4,14}.
+ * ctu_dice_ce_fwd accumulates sums = double [B][C][3] (sum p*y, sum p^2, sum y) followed by ONE double, the sum over
+ * all voxels of -log softmax[label] (zeroed by the caller).  ctu_dice_ce_bwd writes
+ *   dlogits_c = p_c * (a_c - sum_k a_k p_k) + ce_scale * (p_c - y_c),  a_k = coef[b][k][0] * y_k + coef[b][k][1] * p_k
+ * with coef fp32 [B][C][2] and ce_scale (device scalar) built by the caller from the forward sums and the upstream
+ * gradient. */
+int ctu_dice_ce_fwd(const float* logits, const float* target, int B, int C, long long S, double* sums, void* stream);
+int ctu_dice_ce_bwd(const float* logits, const float* target, int B, int C, long long S, const float* coef,
+                    const float* ce_scale, float* dlogits, void* stream);
+
 /* Number of kernels this library has launched since load (bench.py's "gpu_launches"). */
 int64_t ctu_launch_count(void);
 /* 1 if the current device is sm_100 and the driver entry points needed for TMA were found. */

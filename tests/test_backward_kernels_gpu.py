@@ -334,3 +334,21 @@ def test_attention_backward(mode, D, heads):
         dbias_t = torch.zeros(heads * n * n, device="cuda")
         ops.colsum(ds.reshape(tbl.shape[0], -1), dbias_t)
         assert rel(dbias_t.reshape(heads, n, n).transpose(1, 2), br.grad) < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------- fused Dice-CE loss
+@pytest.mark.parametrize("shape", [(2, 14, 12, 10, 16), (1, 14, 24, 24, 48)])
+def test_fused_dice_ce_matches_oracle(shape):
+    from hybrid_ctunet_b200.losses import DiceCELoss
+    from oracle import train_oracle as T
+    torch.manual_seed(5)
+    logits = (torch.randn(*shape, device="cuda") * 2).requires_grad_()
+    target = torch.randint(0, 14, (shape[0], 1) + shape[2:], device="cuda").float()
+    lf = DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6)
+    loss = lf(logits, target)
+    (loss * 3.0).backward()
+    ref_in = logits.detach().double().requires_grad_()
+    ref = T.dice_ce_loss(ref_in, target)
+    (ref * 3.0).backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    assert rel(logits.grad, ref_in.grad) < 1e-4
