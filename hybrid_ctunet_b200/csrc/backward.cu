@@ -406,20 +406,22 @@ __global__ void __launch_bounds__(256) pwa_fuse_bwd_kernel(const __nv_bfloat16* 
 
 // ------------------------------------------------------------------------------------------------
 // out[c] += sum over rows of x[row][c]  (bias gradients, position-embedding gradient, relative-position bias
-// gradient summed over windows).  Block = 32 column vectors x 8 row lanes; grid.y splits the rows.
-template <typename T>
+// gradient summed over windows).  A block covers CW column vectors x (256 / CW) row lanes — CW = 8 for the narrow
+// matrices of the bias gradients (so that every lane loads), 32 otherwise; grid.y splits the rows.
+template <typename T, int CW>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long long ldx, long long M, long long N,
                                                      float* __restrict__ out) {
   constexpr int V = sizeof(T) == 2 ? 8 : 4;
-  __shared__ float red[8][32][V];
-  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-  const long long cvec = (long long)blockIdx.x * 32 + cl;
+  constexpr int RL = 256 / CW;
+  __shared__ float red[RL][CW][V];
+  const int cl = threadIdx.x % CW, rl = threadIdx.x / CW;
+  const long long cvec = (long long)blockIdx.x * CW + cl;
   const long long nvec = N / V;
   float acc[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) acc[j] = 0.f;
   if (cvec < nvec) {
-    for (long long r = (long long)blockIdx.y * 8 + rl; r < M; r += (long long)gridDim.y * 8) {
+    for (long long r = (long long)blockIdx.y * RL + rl; r < M; r += (long long)gridDim.y * RL) {
       if constexpr (sizeof(T) == 2) {
         float f[8];
         ld8(reinterpret_cast<const __nv_bfloat16*>(x) + r * ldx + cvec * 8, f);
@@ -438,8 +440,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s += red[i][cl][j];
+      for (int i = 0; i < RL; ++i) s += red[i][cl][j];
       atomicAdd(out + cvec * V + j, s);
     }
   }
@@ -809,16 +810,25 @@ extern "C" int ctu_pwa_fuse_bwd(const void* qkv1, const void* qkv2, const void* 
 extern "C" int ctu_colsum(const void* x, int x_is_f32, long long ldx, long long M, long long N, float* out, void* stream) {
   const int V = x_is_f32 ? 4 : 8;
   if (!x || !out || M <= 0 || N <= 0 || N % V || ldx % V) return CTU_E_BADARG;
-  const long long gx = (N / V + 31) / 32;
+  const long long nvec = N / V;
+  const int cw = nvec <= 8 ? 8 : 32;
+  const long long gx = (nvec + cw - 1) / cw;
   if (gx > 0x7fffffffLL) return CTU_E_BADARG;
-  long long gy = (M + 63) / 64;
+  const int rl = 256 / cw;
+  long long gy = (M + rl * 8 - 1) / (rl * 8);
   const long long cap = ((long long)bw_num_sms() * 16 + gx - 1) / gx;
   if (gy > cap) gy = cap;
   if (gy > 65535) gy = 65535;
   if (gy < 1) gy = 1;
   dim3 grid((unsigned)gx, (unsigned)gy);
-  if (x_is_f32) colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, ldx, M, N, out);
-  else colsum_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, M, N, out);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_is_f32) {
+    if (cw == 8) colsum_kernel<float, 8><<<grid, 256, 0, st>>>((const float*)x, ldx, M, N, out);
+    else colsum_kernel<float, 32><<<grid, 256, 0, st>>>((const float*)x, ldx, M, N, out);
+  } else {
+    if (cw == 8) colsum_kernel<bf16, 8><<<grid, 256, 0, st>>>((const bf16*)x, ldx, M, N, out);
+    else colsum_kernel<bf16, 32><<<grid, 256, 0, st>>>((const bf16*)x, ldx, M, N, out);
+  }
   count_launch();
   return (int)cudaGetLastError();
 }

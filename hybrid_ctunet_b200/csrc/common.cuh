@@ -157,4 +157,20 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+// Column sums over the 32 lanes of a warp for 32 per-lane values: after the call, lane L holds the sum of
+// v[L] over all lanes (31 shuffles instead of 160).
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = upper ? v[i] : v[i + n];
+      const float keep = upper ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 }  // namespace ctu

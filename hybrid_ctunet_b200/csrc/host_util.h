@@ -5,6 +5,8 @@
 #include <atomic>
 #include <stdint.h>
 
+struct ctu_gemm_desc;
+
 namespace ctu {
 
 typedef CUresult (*tma_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -14,5 +16,8 @@ typedef CUresult (*tma_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 // cuTensorMapEncodeTiled, looked up through the runtime so the library does not link against libcuda.
 tma_encode_fn tma_encoder();
 void count_launch(int n = 1);
+
+// 3x3x3 convolution with shared-memory halo reuse (umma_conv3_halo.cu); CTU_E_UNSUPPORTED when not applicable.
+int conv3_halo_dispatch(const ::ctu_gemm_desc* d, cudaStream_t stream);
 
 }  // namespace ctu

@@ -1,0 +1,396 @@
+// Stride-1 "same" 3x3x3 Conv3d as a tcgen05 implicit GEMM with HALO REUSE of the activation operand (sm_100a).
+//
+// umma_gemm_kernel fetches one 128-voxel x 64-channel box per filter tap: 27 boxes (432 KB) per output tile, which
+// makes the 64-channel layers bound by the L2 -> shared-memory port, not by the tensor pipe.  Here an output tile is
+// 8 (z) x 16 (y) voxels of one x-plane and the producer loads, per x-tap and 64-channel block, ONE halo box of
+// 10 x 18 voxels (23 KB).  All nine (y, z) taps of that plane are then shifted VIEWS of the same shared-memory tile:
+// rows are 128-byte voxel lines, an 8-voxel z-run of output row y is the 8-row group starting at row
+// (y + ty) * 10 + tz, so the K-major SWIZZLE_128B descriptor of tap (ty, tz) is the tile base + (ty*10 + tz) * 128
+// bytes with a stride-byte-offset of 1280 between groups (the swizzle is a function of the shared-memory address, so
+// TMA's writes and the shifted tensor-core reads agree).  Activation traffic drops 6.4x (3 x 22.5 KB instead of
+// 27 x 16 KB per tile); the weights (one 64 x BN box per tap) stream through their own ring.
+// Epilogue: bf16 rows through a swizzled staging tile + TMA store, InstanceNorm statistics (fp64 atomics), as in
+// umma_gemm.cu.  Used for the 64/128-channel layers whose (z, y) extents are multiples of (8, 16).
+#include "common.cuh"
+#include "../../include/ctunet_b200.h"
+#include "host_util.h"
+#include <stdlib.h>
+
+namespace ctu {
+
+constexpr int HALO_Z = 10, HALO_Y = 18;
+constexpr int HALO_A_BYTES = HALO_Z * HALO_Y * 128;  // 23040 bytes written by TMA
+constexpr int HALO_A_STAGE = 23 * 1024;              // ring pitch (1024-byte aligned)
+constexpr int HALO_SLAB_BYTES = 128 * 128;
+
+struct HaloParams {
+  int T1, T2, d1, d2, d3, d4;
+  int n_tiles, total_tiles, cblocks, a_c;
+  double* stats;
+  int n_real, stats_ld;
+  int base_offset_mode;
+};
+
+struct HaloTile {
+  int z0, y0, x, b, n0;
+};
+
+__device__ __forceinline__ HaloTile halo_decode(const HaloParams& p, int tile, int bn) {
+  HaloTile t;
+  const int n_tile = tile % p.n_tiles;
+  int m = tile / p.n_tiles;
+  t.z0 = (m % p.T1) * 8; m /= p.T1;
+  t.y0 = (m % p.T2) * 16; m /= p.T2;
+  t.x = m % p.d3;
+  t.b = m / p.d3;
+  t.n0 = n_tile * bn;
+  return t;
+}
+
+__device__ __forceinline__ uint64_t halo_desc_a(uint32_t saddr, int base_offset_mode) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((HALO_Z * 128) >> 4) << 32;  // 8-row groups are one halo line (10 rows) apart
+  d |= (uint64_t)1 << 46;
+  if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN, int SA, int SB, int CTAS_PER_SM>
+__global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                      const __grid_constant__ CUtensorMap tmB,
+                                                                      const __grid_constant__ CUtensorMap tmC,
+                                                                      const HaloParams p) {
+  constexpr int B_STAGE_BYTES = BN * 128;
+  constexpr int SLABS = BN / 64;
+  constexpr int TMEM_COLS = 2 * BN;
+  constexpr uint32_t IDESC = umma_idesc_bf16(128, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + SA * HALO_A_STAGE;
+  uint8_t* smem_c = smem_b + SB * B_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + SLABS * HALO_SLAB_BYTES);
+  uint64_t* full_a = bars;
+  uint64_t* empty_a = bars + SA;
+  uint64_t* full_b = bars + 2 * SA;
+  uint64_t* empty_b = bars + 2 * SA + SB;
+  uint64_t* bar_tfull = bars + 2 * SA + 2 * SB;
+  uint64_t* bar_tempty = bar_tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  float2* stat_scratch = reinterpret_cast<float2*>(tmem_slot + 2);  // [4][BN]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int s = 0; s < SA; ++s) { mbar_init(smem_u32(&full_a[s]), 1); mbar_init(smem_u32(&empty_a[s]), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(smem_u32(&full_b[s]), 1); mbar_init(smem_u32(&empty_b[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bar_tfull[s]), 1); mbar_init(smem_u32(&bar_tempty[s]), 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t ia = 0, ib = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const HaloTile t = halo_decode(p, tile, BN);
+        for (int t3 = 0; t3 < 3; ++t3) {
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            {
+              const int s = ia % SA;
+              mbar_wait(smem_u32(&empty_a[s]), ((ia / SA) & 1) ^ 1);
+              const uint32_t full = smem_u32(&full_a[s]);
+              mbar_expect_tx(full, HALO_A_BYTES);
+              tma_load_5d(smem_u32(smem_a + s * HALO_A_STAGE), &tmA, full, cb * 64, t.z0 - 1, t.y0 - 1, t.x + t3 - 1, t.b);
+              ++ia;
+            }
+            for (int t21 = 0; t21 < 9; ++t21) {
+              const int tap = t3 * 9 + t21;
+              const int s = ib % SB;
+              mbar_wait(smem_u32(&empty_b[s]), ((ib / SB) & 1) ^ 1);
+              const uint32_t full = smem_u32(&full_b[s]);
+              mbar_expect_tx(full, B_STAGE_BYTES);
+              tma_load_2d(smem_u32(smem_b + s * B_STAGE_BYTES), &tmB, full, tap * p.a_c + cb * 64, t.n0);
+              ++ib;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t ia = 0, ib = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        const int slot = lt & 1;
+        mbar_wait(smem_u32(&bar_tempty[slot]), ((lt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(slot * BN);
+        uint32_t first = 1;
+        for (int t3 = 0; t3 < 3; ++t3) {
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            const int sa = ia % SA;
+            mbar_wait(smem_u32(&full_a[sa]), (ia / SA) & 1);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(smem_a + sa * HALO_A_STAGE);
+            for (int t2 = 0; t2 < 3; ++t2) {
+#pragma unroll
+              for (int t1 = 0; t1 < 3; ++t1) {
+                const int sb = ib % SB;
+                mbar_wait(smem_u32(&full_b[sb]), (ib / SB) & 1);
+                tc_fence_after();
+                const uint64_t da = halo_desc_a(a_base + (uint32_t)((t2 * HALO_Z + t1) * 128), p.base_offset_mode);
+                const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + sb * B_STAGE_BYTES));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16(acc, da + 2 * k, db + 2 * k, IDESC, (first && k == 0) ? 0u : 1u);
+                }
+                first = 0;
+                umma_commit(smem_u32(&empty_b[sb]));
+                ++ib;
+              }
+            }
+            umma_commit(smem_u32(&empty_a[sa]));
+            ++ia;
+          }
+        }
+        umma_commit(smem_u32(&bar_tfull[slot]));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int e = threadIdx.x - 64;
+    const int i1 = r & 7, i2 = r >> 3;
+    constexpr int STAT_PER_THREAD = (BN + 127) / 128;
+    float acc_s[STAT_PER_THREAD], acc_q[STAT_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < STAT_PER_THREAD; ++k) acc_s[k] = acc_q[k] = 0.f;
+    int stat_batch = -1;
+    const int n0_cta = (blockIdx.x % p.n_tiles) * BN;
+    auto flush_stats = [&](int b) {
+      if (b < 0) return;
+#pragma unroll
+      for (int k = 0; k < STAT_PER_THREAD; ++k) {
+        const int c = e + 128 * k;
+        if (c < BN && n0_cta + c < p.n_real) {
+          double* dst = p.stats + ((long long)b * p.stats_ld + n0_cta + c) * 2;
+          atomicAdd(dst, (double)acc_s[k]);
+          atomicAdd(dst + 1, (double)acc_q[k]);
+        }
+        acc_s[k] = acc_q[k] = 0.f;
+      }
+    };
+
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const int slot = lt & 1;
+      const HaloTile t = halo_decode(p, tile, BN);
+      const bool valid = (t.z0 + i1 < p.d1) && (t.y0 + i2 < p.d2);
+      mbar_wait(smem_u32(&bar_tfull[slot]), (lt >> 1) & 1);
+      tc_fence_after();
+      // the staging tile must have been read by the previous TMA store; the statistics scratch must be free
+      if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      named_bar_sync(1, 128);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t raw[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN + c0), raw);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
+        const uint32_t base = smem_u32(smem_c) + (uint32_t)((c0 >> 6) * HALO_SLAB_BYTES + r * 128);
+        const int cbk = (c0 & 63) >> 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t addr = base + (uint32_t)(((cbk + i) ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
+                       "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                       : "memory");
+        }
+        if (p.stats != nullptr) {
+          float v[32], sq[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 f = unpack_bf16x2(pk[j]);
+            v[2 * j] = valid ? f.x : 0.f;
+            v[2 * j + 1] = valid ? f.y : 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+          const float s_sum = warp_transpose_reduce(v, lane);
+          const float s_sq = warp_transpose_reduce(sq, lane);
+          stat_scratch[q * BN + c0 + lane] = make_float2(s_sum, s_sq);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[slot]));
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      named_bar_sync(2, 128);
+      if (e == 0) {
+#pragma unroll
+        for (int sl = 0; sl < SLABS; ++sl) {
+          if (t.n0 + sl * 64 < p.n_real) {
+            asm volatile(
+                "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(&tmC),
+                "r"(smem_u32(smem_c + sl * HALO_SLAB_BYTES)), "r"(t.n0 + sl * 64), "r"(t.z0), "r"(t.y0), "r"(t.x), "r"(t.b)
+                : "memory");
+          }
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (p.stats != nullptr) {
+        if (t.b != stat_batch) {
+          flush_stats(stat_batch);
+          stat_batch = t.b;
+        }
+#pragma unroll
+        for (int k = 0; k < STAT_PER_THREAD; ++k) {
+          const int c = e + 128 * k;
+          if (c < BN) {
+            const float2 s0 = stat_scratch[c], s1 = stat_scratch[BN + c], s2 = stat_scratch[2 * BN + c],
+                         s3 = stat_scratch[3 * BN + c];
+            acc_s[k] += (s0.x + s1.x) + (s2.x + s3.x);
+            acc_q[k] += (s0.y + s1.y) + (s2.y + s3.y);
+          }
+        }
+      }
+    }
+    if (p.stats != nullptr) flush_stats(stat_batch);
+    if (e == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+static int halo_sm_count() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  return n;
+}
+
+template <int BN, int SA, int SB, int CTAS_PER_SM>
+static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const HaloParams& p,
+                       cudaStream_t stream) {
+  constexpr int smem = 1024 + SA * HALO_A_STAGE + SB * BN * 128 + (BN / 64) * HALO_SLAB_BYTES + (2 * SA + 2 * SB + 4) * 8 +
+                       16 + 4 * BN * 8;
+  static_assert(CTAS_PER_SM * (smem + 1024) <= 228 * 1024, "shared memory budget");
+  static_assert(CTAS_PER_SM * 2 * BN <= 512, "TMEM budget");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3_halo_kernel<BN, SA, SB, CTAS_PER_SM>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  int cap = halo_sm_count() * CTAS_PER_SM;
+  if (cap > p.n_tiles) cap -= cap % p.n_tiles;
+  const int grid = p.total_tiles < cap ? p.total_tiles : cap;
+  conv3_halo_kernel<BN, SA, SB, CTAS_PER_SM><<<grid, 192, smem, stream>>>(tmA, tmB, tmC, p);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// Returns CTU_E_UNSUPPORTED when the problem does not fit this kernel (the caller then uses umma_gemm_kernel).
+int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
+  // CTU_CONV_HALO=0 switches this kernel off (A/B comparisons).  Measured on B200, batch 2 (profiles/r01_halo_sweep.txt):
+  // 64->64 @96^3 744 -> 1008 TFLOP/s, 128->64 @96^3 782 -> 1074, 128->128 @48x48x96 1035 -> 1298.
+  // (Setting the descriptor's base-offset field for the shifted views gives WRONG results: the hardware applies the
+  // swizzle to the absolute shared-memory address, so the field stays 0.)
+  static const int mode = [] { const char* e = getenv("CTU_CONV_HALO"); return e ? atoi(e) : 1; }();
+  if (mode == 0) return CTU_E_UNSUPPORTED;
+  if (d->k1 != 3 || d->k2 != 3 || d->k3 != 3) return CTU_E_UNSUPPORTED;
+  if (d->out_mode != CTU_OUT_BF16_ROWS || d->bias || d->residual || d->act != CTU_ACT_NONE || d->convt_cout > 0)
+    return CTU_E_UNSUPPORTED;
+  if (d->block_n != 64 && d->block_n != 128) return CTU_E_UNSUPPORTED;
+  if (d->d1 % 8 != 0 || d->d2 % 16 != 0 || d->a_c % 64 != 0 || d->n_real % 64 != 0) return CTU_E_UNSUPPORTED;
+  if (!tma_encoder()) return CTU_E_DRIVER;
+  const CUtensorMapL2promotion l2p = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  CUtensorMap tmA, tmB, tmC;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)d->a_c, (cuuint64_t)d->d1, (cuuint64_t)d->d2, (cuuint64_t)d->d3, (cuuint64_t)d->d4};
+    cuuint64_t strides[4];
+    strides[0] = (cuuint64_t)d->lda * 2;
+    strides[1] = strides[0] * d->d1;
+    strides[2] = strides[1] * d->d2;
+    strides[3] = strides[2] * d->d3;
+    cuuint32_t box[5] = {64, HALO_Z, HALO_Y, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    if (tma_encoder()(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->a), dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return CTU_E_DRIVER;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d->k_total, (cuuint64_t)d->n_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)d->k_total * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)d->block_n};
+    cuuint32_t es[2] = {1, 1};
+    if (tma_encoder()(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w), dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return CTU_E_DRIVER;
+  }
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)d->n_real, (cuuint64_t)d->d1, (cuuint64_t)d->d2, (cuuint64_t)d->d3, (cuuint64_t)d->d4};
+    cuuint64_t strides[4];
+    strides[0] = (cuuint64_t)d->ldc * 2;
+    strides[1] = strides[0] * d->d1;
+    strides[2] = strides[1] * d->d2;
+    strides[3] = strides[2] * d->d3;
+    cuuint32_t box[5] = {64, 8, 16, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    void* base = reinterpret_cast<__nv_bfloat16*>(d->out) + d->out_col0;
+    if (tma_encoder()(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return CTU_E_DRIVER;
+  }
+  HaloParams p;
+  p.T1 = d->d1 / 8;
+  p.T2 = d->d2 / 16;
+  p.d1 = d->d1; p.d2 = d->d2; p.d3 = d->d3; p.d4 = d->d4;
+  p.n_tiles = d->n_pad / d->block_n;
+  p.cblocks = d->a_c / 64;
+  p.a_c = d->a_c;
+  p.stats = d->stats; p.n_real = d->n_real; p.stats_ld = d->stats_ld;
+  p.base_offset_mode = 0;
+  const long long tiles = (long long)p.T1 * p.T2 * d->d3 * d->d4 * p.n_tiles;
+  if (tiles <= 0 || tiles > 0x7fffffffLL) return CTU_E_BADARG;
+  p.total_tiles = (int)tiles;
+  static const int variant = [] { const char* e = getenv("CTU_CONV_HALO_VARIANT"); return e ? atoi(e) : 0; }();
+  // several small CTAs per SM (one halo stage each) beat fewer CTAs with deeper rings: 3 x <64,1,4> reaches 1008
+  // TFLOP/s where 2 x <64,2,5> reaches 895 and 1 x <64,3,8> 483
+  if (d->block_n == 64) {
+    if (variant == 2) return launch_halo<64, 2, 5, 2>(tmA, tmB, tmC, p, stream);
+    return launch_halo<64, 1, 4, 3>(tmA, tmB, tmC, p, stream);
+  }
+  if (variant == 2) return launch_halo<128, 2, 4, 1>(tmA, tmB, tmC, p, stream);
+  return launch_halo<128, 1, 3, 2>(tmA, tmB, tmC, p, stream);
+}
+
+}  // namespace ctu

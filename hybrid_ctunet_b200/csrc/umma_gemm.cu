@@ -81,22 +81,6 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erf_v);
 }
 
-// Column sums over the 32 lanes of a warp for 32 per-lane values: after the call, lane L holds the sum of
-// v[L] over all lanes (31 shuffles instead of 160).
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < n; ++i) {
-      const float send = upper ? v[i] : v[i + n];
-      const float keep = upper ? v[i + n] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
-
 template <int BN, int STAGES, int OUT_BUFS, int CTAS_PER_SM>
 __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB,
@@ -494,6 +478,10 @@ extern "C" int ctu_umma_gemm(const ctu_gemm_desc* d, void* stream_) {
   }
   if (d->stats != nullptr && d->out_mode == CTU_OUT_F32_CF) return CTU_E_UNSUPPORTED;
   if (!tma_encoder()) return CTU_E_DRIVER;
+  if (d->k1 == 3) {  // large 64/128-channel layers: halo-reuse kernel
+    const int rc = conv3_halo_dispatch(d, stream);
+    if (rc != CTU_E_UNSUPPORTED) return rc;
+  }
 
   const CUtensorMapL2promotion l2p = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   CUtensorMap tmA, tmB, tmC;
