@@ -35,6 +35,19 @@ def rel_pos_index(w: int) -> torch.Tensor:
     return (rel * torch.tensor([(2 * w - 1) ** 2, 2 * w - 1, 1])).sum(-1)
 
 
+_REL_INDEX_CACHE: Dict[tuple, torch.Tensor] = {}
+
+
+def rel_pos_index_on(w: int, device) -> torch.Tensor:
+    """rel_pos_index(w) resident on `device` (cached: no host-to-device copy inside a CUDA-graph capture)."""
+    key = (w, str(device))
+    t = _REL_INDEX_CACHE.get(key)
+    if t is None:
+        t = rel_pos_index(w).to(device)
+        _REL_INDEX_CACHE[key] = t
+    return t
+
+
 def _pad64(v: int) -> int:
     return max(v, 64)
 
@@ -190,14 +203,14 @@ class WeightCache:
 
     def rel_bias(self, name: str, w: int = 6) -> torch.Tensor:
         def build(emb):
-            idx = rel_pos_index(w).to(emb.device)
+            idx = rel_pos_index_on(w, emb.device)
             return emb[idx].permute(2, 0, 1).contiguous().float()
         return self._get("rb:" + name, [name + ".weight"], build)
 
     def rel_bias_t(self, name: str, w: int = 6) -> torch.Tensor:
         """[heads][key][query] copy for the attention backward kernel."""
         return self._get("rbT:" + name, [name + ".weight"],
-                         lambda emb: emb[rel_pos_index(w).to(emb.device)].permute(2, 1, 0).contiguous().float())
+                         lambda emb: emb[rel_pos_index_on(w, emb.device)].permute(2, 1, 0).contiguous().float())
 
     def f32(self, name: str) -> torch.Tensor:
         return self._get("f:" + name, [name], lambda p: p.float().contiguous())
@@ -287,6 +300,9 @@ class Engine:
 
     # ------------------------------------------------------------------ tape plumbing (training only)
     def begin_training_forward(self):
+        # a training forward always re-packs the weights: optimizers that update parameters through fused multi-tensor
+        # kernels (torch.optim.AdamW(fused=True)) do not bump Tensor._version, which is what WeightCache keys on
+        self.w._cache.clear()
         self.tape = Tape()
         self.stats = StatsArena(self.dev, 1 << 20)  # owned by this tape: the backward reads the forward's statistics
         if self.bsums is None:
@@ -408,7 +424,7 @@ class Engine:
                 put(name, buf.reshape(-1)[:p.numel()])
             elif kind == "relbias":  # buf [heads, key, query] -> embedding [(2w-1)^3, heads]
                 p = self.w.params[(name + ".weight").lstrip(".")]
-                idx = rel_pos_index(meta).to(self.dev).reshape(-1)
+                idx = rel_pos_index_on(meta, self.dev).reshape(-1)
                 g = torch.zeros(p.shape, dtype=F32, device=self.dev)
                 g.index_add_(0, idx, buf.permute(2, 1, 0).reshape(-1, p.shape[1]))
                 put(name + ".weight", g)

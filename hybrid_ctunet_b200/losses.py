@@ -108,6 +108,18 @@ def zoom_indices(n_in: int, n_out: int) -> Tuple[int, ...]:
     return tuple(int(v) for v in np.floor(pos + 0.5).astype(np.int64))
 
 
+_ZOOM_DEVICE_CACHE = {}
+
+
+def _zoom_index_tensor(n_in: int, n_out: int, device) -> torch.Tensor:
+    key = (n_in, n_out, str(device))
+    t = _ZOOM_DEVICE_CACHE.get(key)
+    if t is None:  # cached on the device: no host-to-device copy inside a CUDA-graph capture
+        t = torch.as_tensor(zoom_indices(n_in, n_out), device=device)
+        _ZOOM_DEVICE_CACHE[key] = t
+    return t
+
+
 def zoom_nearest(target: torch.Tensor, zoom: Sequence[float]) -> torch.Tensor:
     """ndimage.zoom(target, zoom, order=0, prefilter=False) on the device (axes are independent)."""
     out = target
@@ -115,8 +127,7 @@ def zoom_nearest(target: torch.Tensor, zoom: Sequence[float]) -> torch.Tensor:
         n_in = target.shape[ax]
         n_out = int(round(n_in * z))
         if n_out != n_in:
-            idx = torch.as_tensor(zoom_indices(n_in, n_out), device=target.device)
-            out = out.index_select(ax, idx)
+            out = out.index_select(ax, _zoom_index_tensor(n_in, n_out, target.device))
     return out
 
 

@@ -34,7 +34,10 @@ class Program:
         self.in_acts = list(in_acts)
         self.out_acts = list(out_acts)
         self.converted = converted
-        self.outputs = [from_cl(o) for o in out_acts] if converted else list(out_acts)
+        # tensors handed to the caller are never the engine-side objects the tape closures hold: autograd attaches its
+        # node to the returned objects, and node -> ctx -> tape -> closure -> tensor -> node would be a reference cycle
+        # that keeps the whole step (and its AccumulateGrad nodes) alive until the garbage collector runs
+        self.outputs = [from_cl(o) for o in out_acts] if converted else [o.detach() for o in out_acts]
 
 
 class _EngineFn(torch.autograd.Function):
@@ -54,7 +57,9 @@ class _EngineFn(torch.autograd.Function):
         ctx.in_shapes = [t.shape for t in tensors[:n_in]]
         ctx.names = [n for n, _ in module.named_parameters()]
         eng.tape = None  # a later inference call on the same module must not extend this tape
-        return tuple(prog.outputs)
+        outs = tuple(prog.outputs)
+        prog.outputs = None
+        return outs
 
     @staticmethod
     def backward(ctx, *grad_outputs):
@@ -98,6 +103,22 @@ class KernelModule(nn.Module):
         else:
             eng.w.params = params
         return eng
+
+    def invalidate_weight_cache(self):
+        """Drop the packed bf16 copies of the parameters (they are rebuilt on the next call).  The cache notices
+        parameter updates through Tensor._version (load_state_dict, copy_, non-fused optimizers); every training forward
+        and every train()/eval() switch also drops it, because fused optimizers update parameters without bumping the
+        version.  Call this after any other out-of-band in-place update of the weights between inference calls."""
+        for m in self.modules():
+            eng = getattr(m, "_eng", None)
+            if eng is not None:
+                eng.w._cache.clear()
+
+    def train(self, mode: bool = True):
+        eng = getattr(self, "_eng", None)
+        if eng is not None:
+            eng.w._cache.clear()
+        return super().train(mode)
 
     def _input(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:

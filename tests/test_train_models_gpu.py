@@ -105,3 +105,31 @@ def test_ctunet_training_step():
         loss = ctunet_loss(model(x), y, loss_func)
         loss.backward()
     assert float(loss) < l0, (l0, float(loss))
+
+
+def test_graphed_train_step_trains_with_fused_adamw():
+    """CUDA-graph replay of forward + loss + backward (hybrid_ctunet_b200.training): same loss as the eager step on the
+    same weights, and the packed weights follow a FUSED optimizer (which does not bump Tensor._version)."""
+    from hybrid_ctunet_b200.losses import DiceCELoss, ctunet_loss
+    from hybrid_ctunet_b200.networks.hybrid_CTUNet import CTUNet
+    from hybrid_ctunet_b200.training import GraphedTrainStep
+    torch.manual_seed(0)
+    model = CTUNet(**KW).cuda().train()
+    loss_func = DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6)
+    torch.manual_seed(1)
+    x = torch.rand(1, 1, 96, 96, 96, device="cuda")
+    y = torch.randint(0, 14, (1, 1, 96, 96, 96), device="cuda").float()
+    eager = float(ctunet_loss(model(x), y, loss_func).detach())
+    step = GraphedTrainStep(model, lambda lg, t: ctunet_loss(lg, t, loss_func), x, y, warmup=1)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)
+    losses = []
+    for _ in range(4):
+        losses.append(float(step(x, y).detach()))
+        opt.step()
+    assert abs(losses[0] - eager) < 1e-3 * abs(eager), (losses[0], eager)
+    assert losses[-1] < losses[0] - 1e-2, losses   # the replayed graph sees the updated weights
+    # and so does an eager inference call after the fused updates (train()/eval() drop the packed copies)
+    model.eval()
+    with torch.no_grad():
+        after = float(ctunet_loss(model(x), y, loss_func))
+    assert abs(after - losses[-1]) < 0.2 and after < eager

@@ -13,6 +13,7 @@ from hybrid_ctunet_b200.networks.hybrid_CTUNet import CTUNet  # noqa: E402
 KW = dict(in_channels=1, dim_conv_stem=64, out_channels=14, model_depth=101, img_size=(96, 96), frames=96, patch_frame=8)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+use_graph = len(sys.argv) > 3 and sys.argv[3] == "graph"
 torch.manual_seed(0)
 model = CTUNet(**KW).cuda().train()
 loss_func = DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6)
@@ -40,6 +41,23 @@ def step(timers=None):
         timers.append([ev[i].elapsed_time(ev[i + 1]) for i in range(4)])
     return loss
 
+
+if use_graph:
+    from hybrid_ctunet_b200.training import GraphedTrainStep
+    gstep = GraphedTrainStep(model, lambda lg, t: ctunet_loss(lg, t, loss_func), x, y)
+
+    def step(timers=None):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        loss = gstep(x, y)
+        ev[1].record()
+        opt.step()
+        ev[2].record()
+        if timers is not None:
+            torch.cuda.synchronize()
+            a, b = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+            timers.append([a, 0.0, 0.0, b])
+        return loss
 
 for i in range(2):
     l = step()
