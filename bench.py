@@ -127,9 +127,15 @@ class ConvProbe:
         ms = [a.elapsed_time(b) for a, b in self.pairs]
         avg = sum(ms) / len(ms)
         ach = self.flops / (avg * 1e-3) / 1e12
-        return {"bound": "tensor", "kernel": "umma_gemm_kernel<64,...> as conv3x3x3 64->64 @96^3 (forward + dgrad launches)",
+        traffic, tsrc = None, None
+        prof = os.path.join(ROOT, "profiles", "r01_ncu_full_conv3_halo64.json")
+        if os.path.exists(prof):  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu capture
+            traffic = json.load(open(prof)).get("traffic_bytes_per_launch")
+            tsrc = "profiles/r01_ncu_full_conv3_halo64.json (ncu --set full, same kernel / shape / batch)"
+        return {"bound": "tensor", "kernel": "conv3_halo_kernel<64,1,4,3>: tcgen05 conv3x3x3 64->64 @96^3 (forward + dgrad launches)",
                 "achieved": round(ach, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(ach / peaks["tf_sustained"], 4), "traffic": None, "launches_timed": len(ms),
+                "frac": round(ach / peaks["tf_sustained"], 4), "traffic": traffic, "traffic_source": tsrc,
+                "algorithmic_bytes_per_launch": 2 * 2 * 96 ** 3 * 64 * 2 + 27 * 64 * 64 * 2, "launches_timed": len(ms),
                 "avg_launch_ms": round(avg, 4), "flops_per_launch": self.flops, "peak_source": peaks["src"] + ", sustained"}
 
 

@@ -257,7 +257,8 @@ static int wg_sm_count() {
 }
 
 template <int BN, int J, int SA, int SB, int CTAS_PER_SM>
-static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmY, WgradParams p, int per_slot, cudaStream_t stream) {
+static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmY, WgradParams p, int per_slot, cudaStream_t stream,
+                        int max_splits = 0) {
   constexpr int smem = 1024 + SA * WG_A_STAGE_BYTES + SB * (BN / 64) * WG_SLAB_BYTES + (2 * SA + 2 * SB + 2) * 8 + 16;
   static_assert(CTAS_PER_SM * (smem + 1024) <= 228 * 1024, "shared memory budget");
   static_assert(CTAS_PER_SM * J * BN <= 512, "TMEM budget");
@@ -277,6 +278,9 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmY, WgradPar
   static const int forced = [] { const char* e = getenv("CTU_WGRAD_ITEMS_PER_SLOT"); return e ? atoi(e) : 0; }();
   if (forced > 0) per_slot = forced;
   int splits = (per_slot * slots + base - 1) / base;
+  static const int forced_splits = [] { const char* e = getenv("CTU_WGRAD_SPLITS"); return e ? atoi(e) : 0; }();
+  if (forced_splits > 0) splits = forced_splits;
+  else if (max_splits > 0 && splits > max_splits) splits = max_splits;
   if (splits > p.vox_tiles) splits = p.vox_tiles;
   if (splits < 1) splits = 1;
   p.splits = splits;
@@ -361,7 +365,9 @@ extern "C" int ctu_umma_wgrad(const ctu_wgrad_desc* d, void* stream_) {
       return launch_wgrad<128, 1, 1, 1, 3>(tmX, tmY, p, conv ? 6 : 2, stream);
     case 256:
       if (variant == 1) return launch_wgrad<256, 1, 1, 1, 2>(tmX, tmY, p, 2, stream);
-      return launch_wgrad<256, 2, 2, 2, 1>(tmX, tmY, p, conv && p.vox_tiles >= 400 ? 4 : (conv ? 1 : 2), stream);
+      // ViT-sized GEMMs (7 voxel tiles, 4.7-9.4 MB of dW): the fp32 reductions of the epilogue dominate — at most 3 splits
+      return launch_wgrad<256, 2, 2, 2, 1>(tmX, tmY, p, conv && p.vox_tiles >= 400 ? 4 : (conv ? 1 : 2), stream,
+                                           (!conv && p.vox_tiles <= 8) ? 3 : 0);
     default: return CTU_E_UNSUPPORTED;
   }
 }

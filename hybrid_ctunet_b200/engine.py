@@ -476,9 +476,15 @@ class Engine:
             # input gradient
             if a_needs_grad:
                 pt = self.w.get_t(kind, name, extra)
-                da = self._empty(*a.shape[:-1], ac)
-                ops.gemm(g16, pt, da, dims=dims, a_c=n_eff)
-                self._acc(a, da)
+                cur = self._g(a)
+                if cur is not None and cur.dtype == BF16 and ksize == 1 and cur.shape[-1] == ac:
+                    # a gradient has already arrived for `a` (e.g. through the residual connection): let the GEMM
+                    # epilogue add it instead of running a separate accumulation pass (in place, row for row)
+                    ops.gemm(g16, pt, cur, dims=dims, a_c=n_eff, residual=cur)
+                else:
+                    da = self._empty(*a.shape[:-1], ac)
+                    ops.gemm(g16, pt, da, dims=dims, a_c=n_eff)
+                    self._acc(a, da)
             self._done(out)
         self._rec(bw)
         return out
