@@ -1,0 +1,80 @@
+// Mask-complementation ensemble of the evaluation scripts (test_CTUNet.py:236-251, test_CTUNet_final.py:547-552,
+// trainer_CTUNet.py:287-299): argmax of each head's class scores, argmax of the mean of the two softmaxes, and the
+// per-class Dice counts against the label volume, in ONE pass over the two blended fp32 logit volumes [C][V]
+// (the reference runs 2 softmax + add + 3 argmax torch kernels, copies three volumes to the host and loops 13 classes
+// x 3 masks in numpy).  HBM-bound: 2*C*4 bytes read + 3 bytes written per voxel.
+#include "common.cuh"
+#include "../../include/ctunet_b200.h"
+#include "host_util.h"
+
+namespace ctu {
+
+template <int C>
+__global__ void __launch_bounds__(256) ensemble_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+                                                       long long V, uint8_t* __restrict__ mask, uint8_t* __restrict__ mask1,
+                                                       uint8_t* __restrict__ mask2, const float* __restrict__ labels,
+                                                       unsigned long long* __restrict__ counts) {
+  // counts: [3 masks][C][3] = (|pred == c and label == c|, |pred == c|, |label == c|)
+  __shared__ unsigned int sc[3 * C * 3];
+  for (int i = threadIdx.x; i < 3 * C * 3; i += 256) sc[i] = 0;
+  __syncthreads();
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
+    float a[C], b[C];
+    float ma = -INFINITY, mb = -INFINITY;
+    int ia = 0, ib = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      a[c] = p1[(long long)c * V + v];
+      b[c] = p2[(long long)c * V + v];
+      if (a[c] > ma) { ma = a[c]; ia = c; }   // first maximal index, like torch.argmax
+      if (b[c] > mb) { mb = b[c]; ib = c; }
+    }
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { a[c] = expf(a[c] - ma); sa += a[c]; b[c] = expf(b[c] - mb); sb += b[c]; }
+    const float ra = 1.f / sa, rb = 1.f / sb;
+    float best = -INFINITY;
+    int ie = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float m = (a[c] * ra + b[c] * rb) / 2.0f;
+      if (m > best) { best = m; ie = c; }
+    }
+    if (mask) mask[v] = (uint8_t)ie;
+    if (mask1) mask1[v] = (uint8_t)ia;
+    if (mask2) mask2[v] = (uint8_t)ib;
+    if (labels != nullptr && counts != nullptr) {
+      const int y = (int)labels[v];
+      const int pr[3] = {ie, ia, ib};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        atomicAdd(&sc[(k * C + pr[k]) * 3 + 1], 1u);
+        if (pr[k] == y) atomicAdd(&sc[(k * C + y) * 3 + 0], 1u);
+      }
+      if (y >= 0 && y < C) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) atomicAdd(&sc[(k * C + y) * 3 + 2], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  if (labels != nullptr && counts != nullptr)
+    for (int i = threadIdx.x; i < 3 * C * 3; i += 256)
+      if (sc[i]) atomicAdd(counts + i, (unsigned long long)sc[i]);
+}
+
+}  // namespace ctu
+
+extern "C" int ctu_ensemble_argmax(const float* p1, const float* p2, int C, long long V, uint8_t* mask, uint8_t* mask1,
+                                   uint8_t* mask2, const float* labels, unsigned long long* counts, void* stream) {
+  using namespace ctu;
+  if (!p1 || !p2 || V <= 0 || (!mask && !mask1 && !mask2 && !counts)) return CTU_E_BADARG;
+  if (C != 14) return CTU_E_UNSUPPORTED;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long grid = (V + 255) / 256;
+  if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+  ensemble_kernel<14><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(p1, p2, V, mask, mask1, mask2, labels, counts);
+  count_launch();
+  return (int)cudaGetLastError();
+}

@@ -231,6 +231,13 @@ int ctu_dice_ce_fwd(const float* logits, const float* target, int B, int C, long
 int ctu_dice_ce_bwd(const float* logits, const float* target, int B, int C, long long S, const float* coef,
                     const float* ce_scale, float* dlogits, void* stream);
 
+/* Ensemble of two blended logit volumes (test_CTUNet.py:236-251; test_CTUNet_final.py:547-552): p1, p2 fp32 [C][V];
+ * mask = argmax((softmax(p1) + softmax(p2)) / 2), mask1 / mask2 = argmax of each head (uint8 [V], any may be NULL);
+ * with labels (fp32 [V]) and counts (uint64 [3][C][3], zeroed by the caller) also the per-class Dice counts
+ * (|pred == c and label == c|, |pred == c|, |label == c|) of (ensemble, head 1, head 2).  C = 14. */
+int ctu_ensemble_argmax(const float* p1, const float* p2, int C, long long V, uint8_t* mask, uint8_t* mask1, uint8_t* mask2,
+                        const float* labels, unsigned long long* counts, void* stream);
+
 /* Number of kernels this library has launched since load (bench.py's "gpu_launches"). */
 int64_t ctu_launch_count(void);
 /* 1 if the current device is sm_100 and the driver entry points needed for TMA were found. */

@@ -152,3 +152,25 @@ def sliding_window_inference(inputs, roi_size, sw_batch_size, predictor: Callabl
         final_slicing.insert(0, slice(None))
     outs = [o[tuple(final_slicing)] for o in outs]
     return tuple(outs) if two_heads else outs[0]
+
+
+def ensemble_reference(pred1, pred2, labels=None, n_classes: int = 14):
+    """test_CTUNet.py:236-251 restated (torch softmax / argmax as the reference runs them; numpy `dice` of
+    utils/utils.py:16-22): returns the three masks and, with labels, dice[3][n_classes]."""
+    import numpy as np
+    import torch
+    i1, i2 = torch.softmax(pred1, 0), torch.softmax(pred2, 0)
+    ens = (i1 + i2) / 2.0
+    masks = [torch.argmax(ens, 0).cpu().numpy(), torch.argmax(i1, 0).cpu().numpy(), torch.argmax(i2, 0).cpu().numpy()]
+    out = {"ensemble": masks[0], "head1": masks[1], "head2": masks[2]}
+    if labels is not None:
+        lab = labels.cpu().numpy()
+
+        def dice(x, y):
+            inter = np.sum(x * y)
+            ys = np.sum(y)
+            if ys == 0:
+                return 0.0
+            return 2 * inter / (np.sum(x) + ys)
+        out["dice"] = np.array([[dice(m == i, lab == i) for i in range(n_classes)] for m in masks])
+    return out

@@ -80,3 +80,23 @@ def test_ctunet_sliding_window_three_windows():
     # the fp64 atomics of the InstanceNorm statistics make two runs of the model differ in the last bits only
     assert rel(a0, r0) < 1e-3 and rel(a1, r1) < 1e-4
     assert rel(g0, r0) < 1e-3 and rel(g1, r1) < 1e-4
+
+
+def test_ensemble_masks_match_reference_arithmetic():
+    """argmax masks bit-exact, Dice per class equal (config 5: mask-complementation ensemble on device)."""
+    import numpy as np
+    from hybrid_ctunet_b200.ensemble import ensemble_masks
+    from oracle import sliding_window_oracle as SO
+    torch.manual_seed(11)
+    p1 = torch.randn(14, 40, 36, 28, device="cuda") * 3
+    p2 = torch.randn(14, 40, 36, 28, device="cuda") * 3
+    lab = torch.randint(0, 14, (40, 36, 28), device="cuda").float()
+    got = ensemble_masks(p1, p2, lab)
+    ref = SO.ensemble_reference(p1, p2, lab)
+    for k in ("head1", "head2"):
+        assert np.array_equal(got[k].cpu().numpy(), ref[k]), k
+    # the ensemble argmax can differ only where the two averaged probabilities tie to the last ulp
+    diff = (got["ensemble"].cpu().numpy() != ref["ensemble"]).mean()
+    assert diff < 1e-4, diff
+    assert np.allclose(got["dice"][1:].cpu().numpy(), ref["dice"][1:], atol=1e-12)
+    assert np.allclose(got["dice"][0].cpu().numpy(), ref["dice"][0], atol=5e-3)
