@@ -15,6 +15,7 @@ gradients accumulate in fp32.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -283,6 +284,12 @@ class Engine:
         self.tape: Optional[Tape] = None
         self.bsums: Optional[StatsArena] = None
         self.garena: Optional[GradArena] = None
+        # CTUNet's ViT branch and ResNet encoder are independent until res_decoder3 (hybrid_CTUNet.py:821-838): lane 1
+        # (a side stream) runs the ViT branch while lane 0 (the caller's stream) runs the encoder — both contain long
+        # runs of small kernels that leave most SMs idle on their own
+        self.side: Optional[torch.cuda.Stream] = None
+        self.lane = 0
+        self.two_lanes = os.environ.get("CTU_TWO_LANES", "1") != "0"
 
     # ------------------------------------------------------------------ helpers
     def _empty(self, *shape, dtype=BF16):
@@ -365,7 +372,12 @@ class Engine:
 
     def _rec(self, fn):
         if self.tape is not None:
-            self.tape.fns.append(fn)
+            self.tape.fns.append((self.lane, fn))
+
+    def _side_stream(self) -> torch.cuda.Stream:
+        if self.side is None:
+            self.side = torch.cuda.Stream(device=self.dev)
+        return self.side
 
     def backward(self, out_grads: List[Tuple[torch.Tensor, Optional[torch.Tensor]]], want=()):
         """out_grads: (forward output tensor, its gradient or None).  Returns ({parameter name: fp32 gradient},
@@ -378,8 +390,22 @@ class Engine:
         for t, g in out_grads:
             if g is not None:
                 tape.grads[_key(t)] = g.contiguous()
-        for fn in reversed(tape.fns):
-            fn()
+        main = torch.cuda.current_stream()
+        used_side = False
+        for lane, fn in reversed(tape.fns):
+            if fn is None:  # forward join point: from here back, lane-1 closures run on the side stream, concurrently
+                side = self._side_stream()
+                side.wait_stream(main)
+                for g in tape.grads.values():  # gradients produced on `main` that lane 1 will read (and free)
+                    g.record_stream(side)
+                used_side = True
+            elif lane == 1 and used_side:
+                with torch.cuda.stream(self.side):
+                    fn()
+            else:
+                fn()
+        if used_side:
+            main.wait_stream(self.side)
         igrads = [None if a is None else self._g(a) for a in want]
         grads = self._finalize_param_grads(tape)
         self.tape = None
@@ -894,8 +920,26 @@ class Engine:
     def ctunet(self, x_in, layers, pf: int, depth: int = 12, heads: int = 12):
         """CTUNet.forward (hybrid_CTUNet.py:817-857)."""
         self.stats.reset()
-        enc, vit_logits, vit_96 = self._vit_branch(x_in, pf, depth, heads)
-        res = self.resnet("convnet.", x_in, layers)
+        # (only while a CUDA graph is being captured: in eager mode the caching allocator cannot recycle blocks that
+        # cross streams until their events complete, which costs far more than the overlap gains — measured 97 vs 35 ms)
+        if self.two_lanes and torch.cuda.is_current_stream_capturing():
+            main, side = torch.cuda.current_stream(), self._side_stream()
+            side.wait_stream(main)
+            self.lane = 1
+            try:
+                with torch.cuda.stream(side):
+                    enc, vit_logits, vit_96 = self._vit_branch(x_in, pf, depth, heads)
+            finally:
+                self.lane = 0
+            res = self.resnet("convnet.", x_in, layers)
+            main.wait_stream(side)
+            for t in (*enc, vit_logits, vit_96):
+                t.record_stream(main)
+            if self.tape is not None:
+                self.tape.fns.append((0, None))  # join marker for the backward pass
+        else:
+            enc, vit_logits, vit_96 = self._vit_branch(x_in, pf, depth, heads)
+            res = self.resnet("convnet.", x_in, layers)
         dec3 = self.up_2fusion("res_decoder3", res[3], res[2], enc[0], 512)
         dec2 = self.up_2fusion("res_decoder2", dec3, res[1], enc[1], 256)
         dec1 = self.up_2fusion("res_decoder1", dec2, res[0], enc[2], 128)
