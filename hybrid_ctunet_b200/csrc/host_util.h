@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 struct ctu_gemm_desc;
+struct ctu_wgrad_desc;
 
 namespace ctu {
 
@@ -19,5 +20,7 @@ void count_launch(int n = 1);
 
 // 3x3x3 convolution with shared-memory halo reuse (umma_conv3_halo.cu); CTU_E_UNSUPPORTED when not applicable.
 int conv3_halo_dispatch(const ::ctu_gemm_desc* d, cudaStream_t stream);
+// its weight-gradient counterpart (umma_wgrad_halo.cu)
+int wgrad_halo_dispatch(const ::ctu_wgrad_desc* d, cudaStream_t stream);
 
 }  // namespace ctu

@@ -309,6 +309,10 @@ extern "C" int ctu_umma_wgrad(const ctu_wgrad_desc* d, void* stream_) {
     return CTU_E_BADARG;
   if (d->block_n != 64 && d->block_n != 128 && d->block_n != 256) return CTU_E_UNSUPPORTED;
   if (!tma_encoder()) return CTU_E_DRIVER;
+  if (d->k1 == 3) {  // 64/128-input-channel layers on the (8,16) tile grid: halo-reuse kernel
+    const int rc = wgrad_halo_dispatch(d, stream);
+    if (rc != CTU_E_UNSUPPORTED) return rc;
+  }
 
   const CUtensorMapL2promotion l2p = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   CUtensorMap tmX, tmY;

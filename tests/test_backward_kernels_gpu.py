@@ -57,7 +57,10 @@ def test_wgrad_strided_operands_and_padded_columns():
 
 
 @pytest.mark.parametrize("B,X,Y,Z,Ci,Co", [(2, 8, 12, 16, 64, 64), (1, 6, 6, 12, 128, 128), (1, 5, 7, 9, 64, 256),
-                                           (2, 12, 12, 24, 64, 128), (1, 4, 4, 8, 256, 256)])
+                                           (2, 12, 12, 24, 64, 128), (1, 4, 4, 8, 256, 256),
+                                           # (z, y) multiples of (8, 16): the halo-reuse wgrad kernel
+                                           (1, 4, 16, 8, 64, 64), (2, 5, 32, 16, 64, 64), (1, 3, 16, 16, 128, 64),
+                                           (1, 3, 32, 8, 128, 128), (1, 4, 16, 8, 64, 128)])
 def test_wgrad_conv3(B, X, Y, Z, Ci, Co):
     from hybrid_ctunet_b200 import ops
     torch.manual_seed(B * X + Ci + Co)
