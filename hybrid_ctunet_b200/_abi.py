@@ -31,6 +31,8 @@ SIGS = {
     "ctu_cast_f32_bf16": (P, L, P, L, L, I, P),
     "ctu_patchify_ln_bwd": (P, I, I, I, I, I, P, P, P, F, P),
     "ctu_ensemble_argmax": (P, P, I, L, P, P, P, P, P, P),
+    "ctu_pack_weights": (P, I, L, P),
+    "ctu_unpack_grads": (P, I, L, P),
     "ctu_dice_ce_fwd": (P, P, I, I, L, P, P),
     "ctu_dice_ce_bwd": (P, P, I, I, L, P, P, P, P),
     "ctu_attention_delta": (P, L, P, L, P, L, I, I, P),

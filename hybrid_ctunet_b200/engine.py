@@ -18,6 +18,7 @@ from __future__ import annotations
 import os
 from typing import Callable, Dict, List, Optional, Tuple
 
+import numpy as np
 import torch
 
 from . import ops
@@ -53,24 +54,133 @@ def _pad64(v: int) -> int:
     return max(v, 64)
 
 
+PACK_LIN, PACK_LIN_T, PACK_CONV3, PACK_CONV3_T, PACK_CONVT, PACK_CONVT_T, PACK_PS, PACK_PS_T, PACK_CIN1, PACK_PS_BIAS, \
+    PACK_VEC = range(11)
+_ITEM_DTYPE = np.dtype([("src", "u8"), ("dst", "u8"), ("kind", "i4"), ("rows", "i4"), ("cols", "i4"), ("a", "i4"),
+                        ("b", "i4"), ("c", "i4"), ("unit0", "i8")])
+
+
+class ItemTable:
+    """Device-resident table of ctu_pack_item for the multi-tensor pack / unpack kernels (include/ctunet_b200.h)."""
+
+    def __init__(self, device):
+        self.dev = device
+        self.rows: List[tuple] = []          # (src_ptr, dst_ptr, kind, rows, cols, a, b, c, n_elements)
+        self.table: Optional[torch.Tensor] = None
+        self.units = 0
+
+    def add(self, src_ptr, dst_ptr, kind, rows, cols, a, b, c, n_elements) -> int:
+        self.rows.append((int(src_ptr), int(dst_ptr), int(kind), int(rows), int(cols), int(a), int(b), int(c), int(n_elements)))
+        self.table = None
+        return len(self.rows) - 1
+
+    def _build(self, rows):
+        arr = np.zeros(len(rows), dtype=_ITEM_DTYPE)
+        unit = 0
+        for i, (src, dst, kind, r, c_, a, b, c, n) in enumerate(rows):
+            arr[i] = (src, dst, kind, r, c_, a, b, c, unit)
+            unit += -(-n // 256)
+        t = torch.from_numpy(arr.view(np.uint8).copy()).to(self.dev)
+        return t, unit
+
+    def device_table(self):
+        if self.table is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("the weight / gradient item table changed during CUDA-graph capture; run one eager "
+                                   "warm-up step first")
+            self.table, self.units = self._build(self.rows)
+        return self.table, self.units
+
+    def run(self, entry: str, only: Optional[int] = None):
+        lib = ops._lib.require_device()
+        if only is not None:
+            t, units = self._build([self.rows[only]])
+            n = 1
+        else:
+            if not self.rows:
+                return
+            t, units = self.device_table()
+            n = len(self.rows)
+        ops.check(getattr(lib, entry)(t.data_ptr(), n, units, torch.cuda.current_stream().cuda_stream), entry)
+
+
 class WeightCache:
     """bf16 kernel-layout copies of the module's fp32 parameters (forward and transposed / tap-flipped for the
-    input-gradient GEMMs), refreshed when a parameter changes."""
+    input-gradient GEMMs).  The copies live in persistent buffers filled by ONE multi-tensor kernel launch
+    (ctu_pack_weights): `refresh_all()` re-packs everything (every training forward, every train()/eval() switch —
+    fused optimizers update parameters without bumping Tensor._version), a single stale entry is re-packed when its
+    parameter's version / storage changed."""
 
     def __init__(self, params: Dict[str, torch.Tensor]):
         self.params = params
-        self._cache: Dict[str, Tuple[tuple, object]] = {}
+        self._cache: Dict[str, list] = {}      # key -> [tag, value, item index or None]
+        self.items: Optional[ItemTable] = None
+
+    def _tag(self, names):
+        ps = [self.params[n.lstrip('.')] for n in names]
+        return ps, tuple((p.data_ptr(), p._version, str(p.device)) for p in ps)
 
     def _get(self, key: str, names, build):
-        ps = [self.params[n.lstrip('.')] for n in names]
-        tag = tuple((p.data_ptr(), p._version, str(p.device)) for p in ps)
+        """torch-built entries (a handful of small tables): rebuilt when a parameter changes."""
+        ps, tag = self._tag(names)
         hit = self._cache.get(key)
         if hit is not None and hit[0] == tag:
             return hit[1]
         with torch.no_grad():
             val = build(*[p.detach() for p in ps])
-        self._cache[key] = (tag, val)
+        self._cache[key] = [tag, val, None, list(names), 1]
         return val
+
+    def _packed(self, key: str, wname: str, kind: int, n: int, k: int, *, a: int, b: int, c: int = 0, ksize: int = 1,
+                a_c: Optional[int] = None, block_n: Optional[int] = None, convt=None, bias_name: Optional[str] = None,
+                bias_repeat: int = 1) -> PackedWeight:
+        """bf16 [n_pad, k_pad] matrix produced by the pack kernel from parameter `wname` with layout map `kind`."""
+        names = [wname] + ([bias_name] if bias_name else [])
+        ps, tag = self._tag(names)
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        w = ps[0].detach()
+        if self.items is None:
+            self.items = ItemTable(w.device)
+        if hit is not None and hit[0][0][0] == tag[0][0] and hit[1].w.device == w.device:
+            pw, idx = hit[1], hit[2]          # same storage, new version: re-pack in place
+        else:
+            bn = block_n or ops.pick_block_n(n)
+            n_pad, k_pad = -(-n // bn) * bn, -(-k // 8) * 8
+            buf = torch.empty((n_pad, k_pad), dtype=BF16, device=w.device)
+            bias = None
+            if bias_name:
+                bias = ps[1].detach().to(F32).contiguous() if bias_repeat == 1 else ps[1].detach().to(F32).repeat(bias_repeat)
+            pw = PackedWeight(buf, n, a_c if a_c is not None else k_pad // (ksize ** 3), ksize, bn, convt, bias)
+            idx = self.items.add(w.data_ptr(), buf.data_ptr(), kind, n_pad, k_pad, a, b, c, n_pad * k_pad)
+        if bias_name and bias_repeat != 1:
+            pw.bias.copy_(ps[1].detach().to(F32).repeat(bias_repeat))
+        self.items.run("ctu_pack_weights", only=idx)
+        self._cache[key] = [tag, pw, idx, names, bias_repeat]
+        return pw
+
+    def refresh_all(self):
+        """Re-pack every registered weight from the parameters' current values with one launch."""
+        for ent in self._cache.values():
+            if ent[2] is not None and self._tag(ent[3])[1][0][0] != self.items.rows[ent[2]][0]:
+                self.clear()  # a parameter's storage was replaced (e.g. module.to()): start over
+                return
+        if self.items is not None:
+            self.items.run("ctu_pack_weights")
+        for key in list(self._cache):
+            ent = self._cache[key]
+            if ent[2] is None:
+                if key.startswith(("d1:", "rb:", "rbT:")):  # small torch-built tables: rebuilt on next use
+                    del self._cache[key]
+                continue
+            if ent[4] != 1:  # pixel-shuffle bias, repeated per sub-voxel
+                ent[1].bias.copy_(self._p(ent[3][1]).detach().to(F32).repeat(ent[4]))
+            ent[0] = self._tag(ent[3])[1]
+
+    def clear(self):
+        self._cache.clear()
+        self.items = None
 
     # -- generic access by (kind, name, extra): forward packing and the packing of the dgrad GEMM
     def get(self, kind: str, name: str, extra=None) -> PackedWeight:
@@ -88,103 +198,66 @@ class WeightCache:
             return self.conv_cin1_tc(name)
         raise KeyError(kind)
 
+    def _p(self, name: str) -> torch.Tensor:
+        return self.params[name.lstrip(".")]
+
     def get_t(self, kind: str, name: str, extra=None) -> PackedWeight:
         """Weight of the input-gradient contraction dA = dOut (*) W^T."""
+        w = self._p(name + ".weight")
         if kind == "lin":
-            def build(w, b=None):
-                n, k = w.shape
-                wt = w.t()
-                if b is not None and n < 64:  # heads: 14 logits -> the 64-channel padded gradient
-                    wt = torch.zeros(k, 64, device=w.device, dtype=w.dtype)
-                    wt[:, :n] = w.t()
-                return ops.pack_matrix(wt)
-            names = [name + ".weight"] + ([name + ".bias"] if extra else [])
-            return self._get("linT:" + name, names, build)
+            n, k = w.shape
+            ncols = 64 if (extra and n < 64) else n   # heads: 14 logits -> the 64-channel padded gradient
+            return self._packed("linT:" + name, name + ".weight", PACK_LIN_T, k, ncols, a=n, b=k)
         if kind == "conv1":
-            def build(w, b=None):
-                co, ci = w.shape[:2]
-                cop, cip = _pad64(co), _pad64(ci)
-                wt = torch.zeros(cip, cop, device=w.device, dtype=w.dtype)
-                wt[:ci, :co] = w.reshape(co, ci).t()
-                return ops.pack_matrix(wt)
-            names = [name + ".weight"] + ([name + ".bias"] if extra else [])
-            return self._get("c1T:" + name, names, build)
+            co, ci = w.shape[:2]
+            return self._packed("c1T:" + name, name + ".weight", PACK_LIN_T, _pad64(ci), _pad64(co), a=co, b=ci)
         if kind == "conv3":
-            def build(w):
-                co, ci = w.shape[:2]
-                cop, cip = _pad64(co), _pad64(ci)
-                wp = torch.zeros(cip, 3, 3, 3, cop, device=w.device, dtype=w.dtype)
-                wp[:ci, ..., :co] = w.flip(2, 3, 4).permute(1, 2, 3, 4, 0)
-                return ops.pack_matrix(wp.reshape(cip, 27 * cop), ksize=3, a_c=cop)
-            return self._get("c3T:" + name, [name + ".weight"], build)
+            co, ci = w.shape[:2]
+            cop, cip = _pad64(co), _pad64(ci)
+            return self._packed("c3T:" + name, name + ".weight", PACK_CONV3_T, cip, 27 * cop, a=co, b=ci, ksize=3, a_c=cop)
         if kind == "convt":
-            def build(w):
-                ci, co, kx, ky, kz = w.shape
-                return ops.pack_matrix(w.permute(2, 3, 4, 1, 0).reshape(kx * ky * kz * co, ci).t())
-            return self._get("ctT:" + name, [name + ".weight"], build)
+            ci, co, kx, ky, kz = w.shape
+            return self._packed("ctT:" + name, name + ".weight", PACK_CONVT_T, ci, kx * ky * kz * co, a=ci, b=co, c=kx * ky * kz)
         if kind == "ps":
-            return self._get("psT:" + name, [name + ".weight", name + ".bias"],
-                             lambda w, b: ops.pack_matrix(self._ps_big(w, extra).t()))
+            co, corg = w.shape
+            k3 = extra[0] * extra[1] * extra[2]
+            return self._packed("psT:" + name, name + ".weight", PACK_PS_T, corg * k3, k3 * co, a=co, b=corg, c=k3)
         raise KeyError(kind)
 
     # -- nn.Linear [N, K] (+bias)
     def linear(self, name: str, bias: bool = True, block_n: Optional[int] = None) -> PackedWeight:
-        names = [name + ".weight"] + ([name + ".bias"] if bias else [])
-        return self._get("lin:" + name, names,
-                         lambda w, b=None: ops.pack_matrix(w, bias=b, block_n=block_n))
+        n, k = self._p(name + ".weight").shape
+        return self._packed("lin:" + name, name + ".weight", PACK_LIN, n, k, a=n, b=k, block_n=block_n,
+                            bias_name=(name + ".bias") if bias else None)
 
     # -- Conv3d 1x1x1 [Cout, Cin, 1,1,1]; channel counts below 64 are zero-padded to 64
     def conv1(self, name: str, bias: bool = False) -> PackedWeight:
-        names = [name + ".weight"] + ([name + ".bias"] if bias else [])
-
-        def build(w, b=None):
-            co, ci = w.shape[:2]
-            w2 = w.reshape(co, ci)
-            if b is None:  # feature convs: pad to the 64-channel granularity of the activation buffers
-                cop, cip = _pad64(co), _pad64(ci)
-                if (cop, cip) != (co, ci):
-                    wp = torch.zeros(cop, cip, device=w.device, dtype=w.dtype)
-                    wp[:co, :ci] = w2
-                    w2 = wp
-            return ops.pack_matrix(w2, bias=b)
-        return self._get("c1:" + name, names, build)
+        co, ci = self._p(name + ".weight").shape[:2]
+        if bias:   # logits heads: no padding of the 14 output channels
+            return self._packed("c1:" + name, name + ".weight", PACK_LIN, co, ci, a=co, b=ci, bias_name=name + ".bias")
+        # feature convs: pad to the 64-channel granularity of the activation buffers
+        return self._packed("c1:" + name, name + ".weight", PACK_LIN, _pad64(co), _pad64(ci), a=co, b=ci)
 
     # -- Conv3d 3x3x3 [Cout, Cin, 3,3,3] -> [Cout, 27*Cin] tap-major
     def conv3(self, name: str) -> PackedWeight:
-        def build(w):
-            co, ci = w.shape[:2]
-            cop, cip = _pad64(co), _pad64(ci)
-            wp = torch.zeros(cop, 3, 3, 3, cip, device=w.device, dtype=w.dtype)
-            wp[:co, ..., :ci] = w.permute(0, 2, 3, 4, 1)
-            return ops.pack_matrix(wp.reshape(cop, 27 * cip), ksize=3, a_c=cip)
-        return self._get("c3:" + name, [name + ".weight"], build)
+        co, ci = self._p(name + ".weight").shape[:2]
+        cop, cip = _pad64(co), _pad64(ci)
+        return self._packed("c3:" + name, name + ".weight", PACK_CONV3, cop, 27 * cip, a=co, b=ci, ksize=3, a_c=cip)
 
     # -- ConvTranspose3d kernel == stride [Cin, Cout, kX, kY, kZ]
     def convt(self, name: str) -> PackedWeight:
-        def build(w):
-            ci, co, kx, ky, kz = w.shape
-            w2 = w.permute(2, 3, 4, 1, 0).reshape(kx * ky * kz * co, ci)
-            return ops.pack_matrix(w2, block_n=64 if co % 128 else 128, convt=(co, kz, ky, kx))
-        return self._get("ct:" + name, [name + ".weight"], build)
+        ci, co, kx, ky, kz = self._p(name + ".weight").shape
+        return self._packed("ct:" + name, name + ".weight", PACK_CONVT, kx * ky * kz * co, ci, a=ci, b=co, c=kx * ky * kz,
+                            block_n=64 if co % 128 else 128, convt=(co, kz, ky, kx))
 
-    @staticmethod
-    def _ps_big(w, factor):
-        co, corg = w.shape
-        k3 = factor[0] * factor[1] * factor[2]
-        big = torch.zeros(k3, co, corg, k3, device=w.device, dtype=w.dtype)
-        for s in range(k3):
-            big[s, :, :, s] = w
-        return big.reshape(k3 * co, corg * k3)
-
-    # -- PixelShuffle + Linear (hybrid_CTUNet.py:404-432) as a transposed-conv-shaped GEMM
+    # -- PixelShuffle + Linear (hybrid_CTUNet.py:404-432) as a transposed-conv-shaped GEMM (block-diagonal weight)
     def pixel_shuffle(self, name: str, factor) -> PackedWeight:
-        def build(w, b):
-            co = w.shape[0]
-            fx, fy, fz = factor
-            k3 = fx * fy * fz
-            return ops.pack_matrix(self._ps_big(w, factor), bias=b.repeat(k3), block_n=64 if co % 128 else 128,
-                                   convt=(co, fz, fy, fx))
-        return self._get("ps:" + name, [name + ".weight", name + ".bias"], build)
+        co, corg = self._p(name + ".weight").shape
+        fx, fy, fz = factor
+        k3 = fx * fy * fz
+        return self._packed("ps:" + name, name + ".weight", PACK_PS, k3 * co, corg * k3, a=co, b=corg, c=k3,
+                            block_n=64 if co % 128 else 128, convt=(co, fz, fy, fx), bias_name=name + ".bias",
+                            bias_repeat=k3)
 
     # -- single-input-channel convs on CUDA cores: fp32 [taps, 64]
     def conv_cin1(self, name: str) -> torch.Tensor:
@@ -193,14 +266,9 @@ class WeightCache:
 
     # -- the same weights as a [Cout, taps padded to 64n] bf16 matrix for the tensor-core path over an im2col operand
     def conv_cin1_tc(self, name: str) -> PackedWeight:
-        def build(w):
-            co = w.shape[0]
-            taps = w[0].numel()
-            kpad = -(-taps // 64) * 64
-            wp = torch.zeros(co, kpad, device=w.device, dtype=w.dtype)
-            wp[:, :taps] = w.reshape(co, taps)
-            return ops.pack_matrix(wp)
-        return self._get("d1tc:" + name, [name + ".weight"], build)
+        w = self._p(name + ".weight")
+        co, taps = w.shape[0], w[0].numel()
+        return self._packed("d1tc:" + name, name + ".weight", PACK_CIN1, co, -(-taps // 64) * 64, a=co, b=taps)
 
     def rel_bias(self, name: str, w: int = 6) -> torch.Tensor:
         def build(emb):
@@ -309,7 +377,7 @@ class Engine:
     def begin_training_forward(self):
         # a training forward always re-packs the weights: optimizers that update parameters through fused multi-tensor
         # kernels (torch.optim.AdamW(fused=True)) do not bump Tensor._version, which is what WeightCache keys on
-        self.w._cache.clear()
+        self.w.refresh_all()
         self.tape = Tape()
         self.stats = StatsArena(self.dev, 1 << 20)  # owned by this tape: the backward reads the forward's statistics
         if self.bsums is None:
@@ -317,6 +385,14 @@ class Engine:
         if self.garena is None:
             n = sum(p.numel() for p in self.w.params.values())
             self.garena = GradArena(self.dev, int(n * 1.15) + (32 << 20))
+
+    def prepare_for_capture(self):
+        """Build the device item tables of the pack / unpack kernels now (a host-to-device copy is not allowed while a
+        CUDA graph is being captured)."""
+        if self.w.items is not None:
+            self.w.items.device_table()
+        if getattr(self, "_gtable", None) is not None:
+            self._gtable.device_table()
 
     def _alias(self, view: torch.Tensor, base: torch.Tensor, c0: int):
         if self.tape is not None:
@@ -411,51 +487,90 @@ class Engine:
         self.tape = None
         return grads, igrads
 
+    def _unpack_torch(self, kind, name, buf, meta) -> Tuple[str, torch.Tensor]:
+        """Gradient accumulator -> parameter layout with torch ops (relative-position tables and repeated parameters;
+        everything else goes through the multi-tensor kernel)."""
+        P = lambda n: self.w.params[n.lstrip(".")]
+        if kind in ("lin", "conv1"):
+            p = P(name + ".weight")
+            return name + ".weight", buf[:p[0].numel(), :p.shape[0]].t().reshape(p.shape)
+        if kind == "conv3":
+            co, ci = P(name + ".weight").shape[:2]
+            return name + ".weight", buf.view(3, 3, 3, buf.shape[0] // 27, -1)[..., :ci, :co].permute(4, 3, 0, 1, 2).contiguous()
+        if kind == "convt":
+            ci, co, kx, ky, kz = P(name + ".weight").shape
+            return name + ".weight", buf.view(ci, kx, ky, kz, co).permute(0, 4, 1, 2, 3).contiguous()
+        if kind == "ps":
+            co, corg = P(name + ".weight").shape
+            k3 = buf.shape[0] // corg
+            return name + ".weight", torch.einsum("csso->oc", buf.view(corg, k3, k3, co)).contiguous()
+        if kind == "ps_bias":
+            co = P(name + ".bias").shape[0]
+            return name + ".bias", buf.view(-1, co).sum(0)
+        if kind == "cin1":
+            p = P(name + ".weight")
+            return name + ".weight", buf[:p[0].numel(), :p.shape[0]].t().reshape(p.shape)
+        if kind == "vec":
+            p = P(name)
+            return name, buf.reshape(-1)[:p.numel()].reshape(p.shape).clone()
+        if kind == "relbias":  # buf [heads, key, query] -> embedding [(2w-1)^3, heads]
+            p = P(name + ".weight")
+            idx = rel_pos_index_on(meta, self.dev).reshape(-1)
+            g = torch.zeros(p.shape, dtype=F32, device=self.dev)
+            g.index_add_(0, idx, buf.permute(2, 1, 0).reshape(-1, p.shape[1]))
+            return name + ".weight", g
+        raise KeyError(kind)
+
     def _finalize_param_grads(self, tape: Tape) -> Dict[str, torch.Tensor]:
-        out: Dict[str, torch.Tensor] = {}
-
-        def put(name, g):
-            name = name.lstrip(".")
-            p = self.w.params[name]
-            g = g.reshape(p.shape)
-            out[name] = g if name not in out else out[name] + g
-
+        """fp32 gradient accumulators (transposed-packed layouts of the wgrad / colsum kernels) -> gradients in the
+        parameters' own layouts: one ctu_unpack_grads launch over a cached device item table."""
+        P = lambda n: self.w.params[n.lstrip(".")]
+        recs, slow, seen = [], [], set()
         for kind, name, buf, meta in tape.wrecs:
-            if kind == "lin":        # buf [K, Npad] -> [N, K]
-                n, k = self.w.params[(name + ".weight").lstrip(".")].shape
-                put(name + ".weight", buf[:k, :n].t())
-            elif kind == "conv1":    # buf [cip, cop] -> [co, ci, 1, 1, 1]
-                co, ci = self.w.params[(name + ".weight").lstrip(".")].shape[:2]
-                put(name + ".weight", buf[:ci, :co].t())
-            elif kind == "conv3":    # buf [27*cip, cop] -> [co, ci, 3, 3, 3]
-                co, ci = self.w.params[(name + ".weight").lstrip(".")].shape[:2]
-                cip = buf.shape[0] // 27
-                put(name + ".weight", buf.view(3, 3, 3, cip, -1)[..., :ci, :co].permute(4, 3, 0, 1, 2))
-            elif kind == "convt":    # buf [ci, k3*co] -> [ci, co, kx, ky, kz]
-                ci, co, kx, ky, kz = self.w.params[(name + ".weight").lstrip(".")].shape
-                put(name + ".weight", buf.view(ci, kx, ky, kz, co).permute(0, 4, 1, 2, 3))
-            elif kind == "ps":       # buf [corg*k3, k3*co]: the k3 diagonal blocks hold the Linear's gradient
-                co, corg = self.w.params[(name + ".weight").lstrip(".")].shape
-                k3 = buf.shape[0] // corg
-                put(name + ".weight", torch.einsum("csso->oc", buf.view(corg, k3, k3, co)))
-            elif kind == "ps_bias":  # buf [k3*co]
-                co = self.w.params[(name + ".bias").lstrip(".")].shape[0]
-                put(name + ".bias", buf.view(-1, co).sum(0))
-            elif kind == "cin1":     # buf [kpad, 64] -> [co, 1, kx, ky, kz]
-                p = self.w.params[(name + ".weight").lstrip(".")]
-                taps = p[0].numel()
-                put(name + ".weight", buf[:taps, :p.shape[0]].t())
-            elif kind == "vec":      # bias / LayerNorm vectors (possibly padded)
-                p = self.w.params[name.lstrip(".")]
-                put(name, buf.reshape(-1)[:p.numel()])
-            elif kind == "relbias":  # buf [heads, key, query] -> embedding [(2w-1)^3, heads]
-                p = self.w.params[(name + ".weight").lstrip(".")]
-                idx = rel_pos_index_on(meta, self.dev).reshape(-1)
-                g = torch.zeros(p.shape, dtype=F32, device=self.dev)
-                g.index_add_(0, idx, buf.permute(2, 1, 0).reshape(-1, p.shape[1]))
-                put(name + ".weight", g)
-            else:  # pragma: no cover
-                raise KeyError(kind)
+            pname = (name if kind == "vec" else name + (".bias" if kind == "ps_bias" else ".weight")).lstrip(".")
+            if kind == "relbias" or pname in seen:
+                slow.append((kind, name, buf, meta))
+                continue
+            seen.add(pname)
+            p = P(pname)
+            ld = int(buf.shape[-1])
+            if kind in ("lin", "conv1"):
+                item = (PACK_LIN, p.shape[0], p[0].numel(), 0)
+            elif kind == "conv3":
+                item = (PACK_CONV3, p.shape[0], p.shape[1], buf.shape[0] // 27)
+            elif kind == "convt":
+                item = (PACK_CONVT, p.shape[0], p.shape[1], p[0, 0].numel())
+            elif kind == "ps":
+                item = (PACK_PS, p.shape[0], p.shape[1], buf.shape[0] // p.shape[1])
+            elif kind == "ps_bias":
+                item = (PACK_PS_BIAS, p.shape[0], 0, buf.numel() // p.shape[0])
+            elif kind == "cin1":
+                item = (PACK_CIN1, p.shape[0], p[0].numel(), 0)
+            else:
+                item = (PACK_VEC, 0, 0, 0)
+            recs.append((pname, buf, ld, item))
+        sig = tuple((pn, buf.data_ptr(), it) for pn, buf, _, it in recs)
+        if getattr(self, "_gsig", None) != sig:
+            total = sum(P(pn).numel() for pn, _, _, _ in recs)
+            self._gflat = torch.empty(total, dtype=F32, device=self.dev)
+            self._gtable = ItemTable(self.dev)
+            self._gviews = []
+            off = 0
+            for pn, buf, ld, (code, a_, b_, c_) in recs:
+                n = P(pn).numel()
+                self._gtable.add(buf.data_ptr(), self._gflat.data_ptr() + 4 * off, code, n, ld, a_, b_, c_, n)
+                self._gviews.append((pn, off, n))
+                off += n
+            self._gsig = sig
+        out: Dict[str, torch.Tensor] = {}
+        if recs:
+            self._gtable.run("ctu_unpack_grads")
+            for pn, off, n in self._gviews:
+                out[pn] = self._gflat[off:off + n].view(P(pn).shape)
+        for kind, name, buf, meta in slow:
+            pn, g = self._unpack_torch(kind, name, buf, meta)
+            pn = pn.lstrip(".")
+            out[pn] = g if pn not in out else out[pn] + g
         return out
 
     # ------------------------------------------------------------------ primitives (forward + recorded backward)

@@ -112,12 +112,12 @@ class KernelModule(nn.Module):
         for m in self.modules():
             eng = getattr(m, "_eng", None)
             if eng is not None:
-                eng.w._cache.clear()
+                eng.w.refresh_all()
 
     def train(self, mode: bool = True):
         eng = getattr(self, "_eng", None)
         if eng is not None:
-            eng.w._cache.clear()
+            eng.w.refresh_all()
         return super().train(mode)
 
     def _input(self, x: torch.Tensor) -> torch.Tensor:

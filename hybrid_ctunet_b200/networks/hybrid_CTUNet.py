@@ -340,6 +340,7 @@ class _Net(KernelModule):
             static_x = x.clone()
             self._run(eng, static_x)  # warm-up: packs weights, sets kernel attributes, primes the allocator
             torch.cuda.synchronize()
+            eng.prepare_for_capture()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 out = self._run(eng, static_x)

@@ -38,8 +38,7 @@ class GraphedTrainStep:
         for p in params:
             p.grad = None
         gc.collect()  # no autograd graph of an earlier eager step (with AccumulateGrad nodes on the default stream) survives
-        eng = model._engine()
-        eng.w._cache.clear()  # every weight is re-packed INSIDE the graph, from the parameters' current values
+        model._engine().prepare_for_capture()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = loss_fn(model(self.x), self.y)

@@ -238,6 +238,41 @@ int ctu_dice_ce_bwd(const float* logits, const float* target, int B, int C, long
 int ctu_ensemble_argmax(const float* p1, const float* p2, int C, long long V, uint8_t* mask, uint8_t* mask1, uint8_t* mask2,
                         const float* labels, unsigned long long* counts, void* stream);
 
+/* Multi-tensor weight packing and gradient unpacking: ONE launch per direction over a DEVICE-resident item table
+ * (the reference keeps a single fp32 layout for cuDNN / cuBLAS; the tensor-core kernels here use packed bf16 layouts
+ * and produce transposed-packed fp32 gradients, so every training step re-packs ~800 matrices and unpacks ~400).
+ * ctu_pack_weights : dst = bf16 [rows][cols] (zero padded), src = fp32 parameter, kind = layout map:
+ *   LIN / LIN_T   (a = N, b = K)            nn.Linear / 1x1x1 conv [N][K] and its transpose
+ *   CONV3 / _T    (a = co, b = ci)          [co][27*cip] tap-major and the tap-flipped [cip][27*cop] of the dgrad
+ *   CONVT / _T    (a = ci, b = co, c = k^3) ConvTranspose3d k == s as [k^3*co][ci] and its transpose
+ *   PS / PS_T     (a = co, b = corg, c = k^3) pixel-shuffle Linear as the block-diagonal [k^3*co][corg*k^3]
+ *   CIN1          (a = co, b = taps)        C_in = 1 convolution as [co][taps padded]
+ * ctu_unpack_grads : dst = fp32 gradient in the parameter's own layout (rows = its element count), src = fp32
+ *   accumulator written by ctu_umma_wgrad / ctu_colsum with row pitch cols; kinds LIN, CONV3 (c = cip), CONVT, PS,
+ *   PS_BIAS (a = co, c = k^3), CIN1, VEC.
+ * unit0 = index of the item's first work unit (256 elements per unit); items sorted by unit0. */
+#define CTU_PACK_LIN 0
+#define CTU_PACK_LIN_T 1
+#define CTU_PACK_CONV3 2
+#define CTU_PACK_CONV3_T 3
+#define CTU_PACK_CONVT 4
+#define CTU_PACK_CONVT_T 5
+#define CTU_PACK_PS 6
+#define CTU_PACK_PS_T 7
+#define CTU_PACK_CIN1 8
+#define CTU_PACK_PS_BIAS 9
+#define CTU_PACK_VEC 10
+typedef struct ctu_pack_item {
+  const void* src;
+  void* dst;
+  int32_t kind;
+  int32_t rows, cols;
+  int32_t a, b, c;
+  int64_t unit0;
+} ctu_pack_item;
+int ctu_pack_weights(const ctu_pack_item* items_dev, int n_items, long long total_units, void* stream);
+int ctu_unpack_grads(const ctu_pack_item* items_dev, int n_items, long long total_units, void* stream);
+
 /* Number of kernels this library has launched since load (bench.py's "gpu_launches"). */
 int64_t ctu_launch_count(void);
 /* 1 if the current device is sm_100 and the driver entry points needed for TMA were found. */
