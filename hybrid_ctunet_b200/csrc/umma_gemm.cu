@@ -18,6 +18,7 @@
 #include "../../include/ctunet_b200.h"
 #include "host_util.h"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace ctu {
 
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
   uint64_t* bar_tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float2* stat_scratch = reinterpret_cast<float2*>(tmem_slot + 2);  // [4][BN]
+  float* bias_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(stat_scratch + 4 * BN) + 15) & ~uintptr_t(15));  // [BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -201,6 +203,10 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
     for (int k = 0; k < STAT_PER_THREAD; ++k) acc_s[k] = acc_q[k] = 0.f;
     int stat_batch = -1;
     const int n0_cta = (blockIdx.x % p.n_tiles) * BN;
+    if (p.bias != nullptr) {  // the grid is a multiple of n_tiles: this CTA only ever sees the N tile n0_cta
+      for (int c = e; c < BN; c += 128) bias_s[c] = (n0_cta + c < p.n_real) ? __ldg(p.bias + n0_cta + c) : 0.f;
+      named_bar_sync(1, 128);
+    }
     auto flush_stats = [&](int b) {
       if (b < 0) return;
 #pragma unroll
@@ -247,8 +253,11 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
         named_bar_sync(1, 128);
       }
 
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += CH) {
+      // One 32-column chunk of the tile.  kFull (every column of the chunk is a real output column — always, except in
+      // the last N tile of the 14-logit heads) folds the per-element range checks away: the HBM-bound GEMMs of this
+      // path (K = 64..512) are otherwise bound by the instruction count of this loop, not by memory.
+      auto chunk = [&](int c0, auto full_tag) {
+        constexpr bool kFull = decltype(full_tag)::value;
         uint32_t raw[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN + c0);
         if constexpr (CH == 32) tmem_ld32(taddr, raw);
@@ -261,10 +270,13 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
         for (int j = CH; j < 32; ++j) v[j] = 0.f;
 
         const int gcol = n0 + c0;  // column in the GEMM's N space (bias / stats / n_real)
-        if (p.bias != nullptr) {
+        if (p.bias != nullptr) {   // staged once per CTA in shared memory, zero beyond n_real
+          const float4* bp = reinterpret_cast<const float4*>(bias_s + c0);
 #pragma unroll
-          for (int j = 0; j < CH; ++j)
-            if (gcol + j < p.n_real) v[j] += __ldg(p.bias + gcol + j);
+          for (int j = 0; j < CH; j += 4) {
+            const float4 bv = bp[j >> 2];
+            v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+          }
         }
         if (p.act == CTU_ACT_GELU) {
 #pragma unroll
@@ -275,7 +287,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
           const float* rp = reinterpret_cast<const float*>(p.residual) + out_row * p.ldr + ocol;
 #pragma unroll
           for (int j = 0; j < CH; j += 4) {
-            if (gcol + j < p.n_real) {
+            if (kFull || gcol + j < p.n_real) {
               const float4 rv = *reinterpret_cast<const float4*>(rp + j);
               v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
             }
@@ -284,7 +296,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
           const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + out_row * p.ldr + ocol;
 #pragma unroll
           for (int j = 0; j < CH; j += 8) {
-            if (gcol + j < p.n_real) {
+            if (kFull || gcol + j < p.n_real) {
               const uint4 rv = *reinterpret_cast<const uint4*>(rp + j);
               float2 f;
               f = unpack_bf16x2(rv.x); v[j] += f.x; v[j + 1] += f.y;
@@ -317,7 +329,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldc + ocol;
 #pragma unroll
             for (int j = 0; j < CH; j += 8) {
-              if (gcol + j < p.n_real)
+              if (kFull || gcol + j < p.n_real)
                 *reinterpret_cast<uint4*>(op + j) = make_uint4(pk[j / 2], pk[j / 2 + 1], pk[j / 2 + 2], pk[j / 2 + 3]);
             }
           }
@@ -335,7 +347,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
             float* op = reinterpret_cast<float*>(p.out) + out_row * p.ldc + ocol;
 #pragma unroll
             for (int j = 0; j < CH; j += 4) {
-              if (gcol + j < p.n_real) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (kFull || gcol + j < p.n_real) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
           }
           if (p.stats != nullptr) {
@@ -349,7 +361,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
             float* op = reinterpret_cast<float*>(p.out) + ((long long)tc.t4 * p.n_real) * S + s_idx;
 #pragma unroll
             for (int j = 0; j < CH; ++j)
-              if (gcol + j < p.n_real) op[(long long)(gcol + j) * S] = v[j];
+              if (kFull || gcol + j < p.n_real) op[(long long)(gcol + j) * S] = v[j];
           }
         }
 
@@ -361,6 +373,11 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
           const float s_sq = warp_transpose_reduce(sq, lane);
           if (lane < CH) stat_scratch[q * BN + c0 + lane] = make_float2(s_sum, s_sq);
         }
+      };
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        if (n0 + c0 + CH <= p.n_real) chunk(c0, std::true_type{});
+        else chunk(c0, std::false_type{});
       }
 
       // accumulator fully read: hand it back to the MMA warp before the (slower) global write-back
@@ -417,7 +434,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
 template <int BN, int STAGES, int OUT_BUFS>
 constexpr int gemm_smem_bytes() {
   return 1024 + STAGES * (A_STAGE_BYTES + BN * BLOCK_K * 2) + OUT_BUFS * (BN / 64) * SLAB_BYTES + (2 * STAGES + 4) * 8 +
-         16 + 4 * BN * 8;
+         16 + 4 * BN * 8 + BN * 4 + 16;
 }
 
 static int sm_count() {

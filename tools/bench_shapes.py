@@ -40,6 +40,9 @@ mk_conv("conv512_512@12", 12, 12, 24, 512, 512)
 mk_conv("conv64_64@48(l1)", 48, 48, 96, 64, 64)
 T1 = B * 48 * 48 * 96
 mk_lin("ffn128_up_gelu", T1, 128, 512, act=1, bias=True)
+mk_lin("ffn128_up_gelu_bn64", T1, 128, 512, act=1, bias=True, bn=64)
+mk_lin("ffn128_up_noact", T1, 128, 512, bias=True)
+mk_lin("ffn128_up_noact_bn64", T1, 128, 512, bias=True, bn=64)
 mk_lin("ffn128_down_res", T1, 512, 128, bias=True, res=True)
 mk_lin("pwa128_qkv", T1, 128, 384)
 mk_lin("pwa128_out", T1, 128, 128)
@@ -49,6 +52,7 @@ mk_lin("vitdec_conv3_128_64@96_stats", B * 96 ** 3, 128, 64, stats=True)
 T2 = B * 24 * 24 * 48
 mk_lin("pwa256_qkv", T2, 256, 768)
 mk_lin("ffn256_up_gelu", T2, 256, 1024, act=1, bias=True)
+mk_lin("ffn256_up_gelu_bn64", T2, 256, 1024, act=1, bias=True, bn=64)
 mk_lin("vit_qkv", B * 432, 768, 2304)
 mk_lin("vit_ffn_up", B * 432, 768, 3072, act=1, bias=True)
 mk_lin("vit2_qkv", 864, 768, 2304)
