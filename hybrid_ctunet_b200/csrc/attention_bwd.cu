@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
   }
 }
 
-template <int D>
-__global__ void __launch_bounds__(128) attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, int C,
+template <int D, int NW, bool DIRECT_DQ>
+__global__ void __launch_bounds__(32 * NW) attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, int C,
                                                             const __nv_bfloat16* __restrict__ dout, int ldd,
                                                             const float* __restrict__ lse, const float* __restrict__ delta,
                                                             const float* __restrict__ biasT, float scale,
@@ -56,8 +56,9 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const __nv_bfloat16*
   __shared__ __align__(16) __nv_bfloat16 dOs[QC * LDQ];
   __shared__ __align__(16) __nv_bfloat16 Qt[D * LDT];
   __shared__ __align__(16) __nv_bfloat16 dOt[D * LDT];
-  __shared__ __align__(16) __nv_bfloat16 Ktw[4][D * LDK];
-  __shared__ __align__(16) __nv_bfloat16 patch[4][16 * LDK];
+  constexpr int NT = 32 * NW;  // threads per CTA: NW warps, 16 keys each
+  __shared__ __align__(16) __nv_bfloat16 Ktw[NW][D * LDK];
+  __shared__ __align__(16) __nv_bfloat16 patch[NW][16 * LDK];
   __shared__ __align__(16) float dQs[QC * D];
   __shared__ float lse_s[QC], delta_s[QC];
   __shared__ long long qrow_s[QC];
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const __nv_bfloat16*
   const float sl = scale * LOG2E;
 
   // ---- this warp's 16 keys: K and V as A fragments (rows = keys), K^T in shared memory for the dQ product
-  const int key0 = kb * 64 + warp * 16;
+  const int key0 = kb * (16 * NW) + warp * 16;
   const int ka = key0 + g, kbk = key0 + g + 8;
   const bool va = ka < n, vb = kbk < n;
   const long long ra = va ? token_row(map, win, ka, n) : 0;
@@ -123,8 +124,8 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const __nv_bfloat16*
       delta_s[tid] = ok ? delta[row * heads + h] : 0.f;
     }
     __syncthreads();
-    for (int i = tid; i < QC * D / 4; i += 128) *reinterpret_cast<float4*>(dQs + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = tid; i < QC * (D / 8); i += 128) {
+    for (int i = tid; i < QC * D / 4; i += NT) *reinterpret_cast<float4*>(dQs + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < QC * (D / 8); i += NT) {
       const int j = i / (D / 8), vi = i % (D / 8);
       const long long row = qrow_s[j];
       uint4 qv = make_uint4(0, 0, 0, 0), gv = make_uint4(0, 0, 0, 0);
@@ -238,16 +239,24 @@ __global__ void __launch_bounds__(128) attention_bwd_kernel(const __nv_bfloat16*
       }
     }
     __syncthreads();
-    // ---- reduce the four warps' dQ partials and add them to the fp32 dQ buffer
-    for (int i = tid; i < QC * (D / 4); i += 128) {
+    // ---- dQ of this chunk, summed over the CTA's warps in dQs: the whole key range lives in this CTA (DIRECT_DQ) ->
+    // final value, written as bf16; otherwise a partial sum added to the fp32 dQ buffer with vector reductions
+    for (int i = tid; i < QC * (D / 4); i += NT) {
       const int j = i / (D / 4), c4 = (i % (D / 4)) * 4;
       const long long row = qrow_s[j];
       if (row < 0) continue;
       const float4 a = *reinterpret_cast<const float4*>(dQs + j * D + c4);
-      float* dst = dq_f32 + row * C + h * D + c4;
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x * scale), "f"(a.y * scale),
-                   "f"(a.z * scale), "f"(a.w * scale)
-                   : "memory");
+      if constexpr (DIRECT_DQ) {
+        uint2 pk;
+        pk.x = pack_bf16x2(a.x * scale, a.y * scale);
+        pk.y = pack_bf16x2(a.z * scale, a.w * scale);
+        *reinterpret_cast<uint2*>(dqkv + row * ld_dqkv + h * D + c4) = pk;
+      } else {
+        float* dst = dq_f32 + row * C + h * D + c4;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x * scale), "f"(a.y * scale),
+                     "f"(a.z * scale), "f"(a.w * scale)
+                     : "memory");
+      }
     }
   }
 
@@ -285,13 +294,14 @@ extern "C" int ctu_attention_delta(const void* o, long long ldo, const void* dou
 }
 
 // qkv / dqkv: bf16 [rows][3C] (q|k|v); dqkv receives dK and dV, dQ is ACCUMULATED into dq_f32 (fp32 [rows][C],
-// zeroed by the caller).  biasT: fp32 [heads][n][n] indexed [key][query] or NULL; ds_out: bf16
+// zeroed by the caller) — except for dim_head 32 with n <= 224 (the 6^3 windows), where dQ is written straight into
+// dqkv[:, :C] and dq_f32 may be NULL.  biasT: fp32 [heads][n][n] indexed [key][query] or NULL; ds_out: bf16
 // [windows][heads][n][n] indexed [key][query] or NULL.
 extern "C" int ctu_attention_bwd(const void* qkv, int ld_qkv, int C, int dim_head, const void* dout, int ldd,
                                  const float* lse, const float* delta, const float* biasT, void* dqkv, int ld_dqkv,
                                  float* dq_f32, void* ds_out, int n, int windows, int mode, int batch, int X, int Y, int Z,
                                  int w, void* stream) {
-  if (!qkv || !dout || !lse || !delta || !dqkv || !dq_f32) return CTU_E_BADARG;
+  if (!qkv || !dout || !lse || !delta || !dqkv) return CTU_E_BADARG;
   if ((dim_head != 32 && dim_head != 64) || C % dim_head || ld_qkv % 8 || ldd % 8 || ld_dqkv % 8 || C % 4) return CTU_E_BADARG;
   if ((biasT || ds_out) && (n % 2)) return CTU_E_BADARG;
   TokenMap m;
@@ -304,17 +314,28 @@ extern "C" int ctu_attention_bwd(const void* qkv, int ld_qkv, int C, int dim_hea
   }
   if (windows <= 0 || windows > 65535) return CTU_E_BADARG;
   const int heads = C / dim_head;
-  dim3 grid((n + 63) / 64, heads, windows);
   const float scale = 1.0f / sqrtf((float)dim_head);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dim_head == 64)
-    attention_bwd_kernel<64><<<grid, 128, 0, st>>>((const __nv_bfloat16*)qkv, ld_qkv, C, (const __nv_bfloat16*)dout, ldd, lse,
-                                                   delta, biasT, scale, (__nv_bfloat16*)dqkv, ld_dqkv, dq_f32,
-                                                   (__nv_bfloat16*)ds_out, n, m);
-  else
-    attention_bwd_kernel<32><<<grid, 128, 0, st>>>((const __nv_bfloat16*)qkv, ld_qkv, C, (const __nv_bfloat16*)dout, ldd, lse,
-                                                   delta, biasT, scale, (__nv_bfloat16*)dqkv, ld_dqkv, dq_f32,
-                                                   (__nv_bfloat16*)ds_out, n, m);
+  const __nv_bfloat16* q = (const __nv_bfloat16*)qkv;
+  const __nv_bfloat16* go = (const __nv_bfloat16*)dout;
+  __nv_bfloat16* dq = (__nv_bfloat16*)dqkv;
+  __nv_bfloat16* ds = (__nv_bfloat16*)ds_out;
+  if (dim_head == 32 && n <= 224) {
+    // 6x6x6 windows: one CTA of 14 warps owns every key of a (window, head): the query chunks are staged once for all
+    // of them and dQ needs neither global reductions nor the fp32 buffer
+    dim3 grid(1, heads, windows);
+    attention_bwd_kernel<32, 14, true><<<grid, 32 * 14, 0, st>>>(q, ld_qkv, C, go, ldd, lse, delta, biasT, scale, dq, ld_dqkv,
+                                                                 nullptr, ds, n, m);
+  } else {
+    if (!dq_f32) return CTU_E_BADARG;
+    dim3 grid((n + 63) / 64, heads, windows);
+    if (dim_head == 64)
+      attention_bwd_kernel<64, 4, false><<<grid, 128, 0, st>>>(q, ld_qkv, C, go, ldd, lse, delta, biasT, scale, dq, ld_dqkv,
+                                                               dq_f32, ds, n, m);
+    else
+      attention_bwd_kernel<32, 4, false><<<grid, 128, 0, st>>>(q, ld_qkv, C, go, ldd, lse, delta, biasT, scale, dq, ld_dqkv,
+                                                               dq_f32, ds, n, m);
+  }
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -1,9 +1,15 @@
 #include "host_util.h"
+#include <stdlib.h>
 #include "../../include/ctunet_b200.h"
 
 namespace ctu {
 
 static std::atomic<int64_t> g_launches{0};
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("CTU_PDL"); return e ? atoi(e) != 0 : false; }();
+  return on;
+}
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

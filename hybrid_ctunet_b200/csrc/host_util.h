@@ -23,4 +23,27 @@ int conv3_halo_dispatch(const ::ctu_gemm_desc* d, cudaStream_t stream);
 // its weight-gradient counterpart (umma_wgrad_halo.cu)
 int wgrad_halo_dispatch(const ::ctu_wgrad_desc* d, cudaStream_t stream);
 
+// Launch with programmatic dependent launch (PDL): the kernel may be scheduled while the previous kernel of the stream
+// is still draining; it must execute pdl_wait() (griddepcontrol.wait) before its first access to global memory that a
+// predecessor may have written, and calls pdl_trigger() early so that ITS successor can do the same.  Saves the
+// launch + prologue latency (barrier init, TMEM allocation, descriptor prefetch) between kernels.  Measured on B200: no
+// gain for this workload (the ~16 us floor of the small GEMMs is not launch latency), so it is OFF unless CTU_PDL=1.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace ctu

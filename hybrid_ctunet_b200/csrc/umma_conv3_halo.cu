@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_kernel(const __gr
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
   float2* stat_scratch = reinterpret_cast<float2*>(tmem_slot + 2);  // [4][BN]
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -311,9 +313,9 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   int cap = halo_sm_count() * CTAS_PER_SM;
   if (cap > p.n_tiles) cap -= cap % p.n_tiles;
   const int grid = p.total_tiles < cap ? p.total_tiles : cap;
-  conv3_halo_kernel<BN, SA, SB, CTAS_PER_SM><<<grid, 192, smem, stream>>>(tmA, tmB, tmC, p);
+  const cudaError_t le = launch_pdl(conv3_halo_kernel<BN, SA, SB, CTAS_PER_SM>, dim3(grid), dim3(192), smem, stream, tmA, tmB, tmC, p);
   count_launch();
-  return (int)cudaGetLastError();
+  return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
 
 // Returns CTU_E_UNSUPPORTED when the problem does not fit this kernel (the caller then uses umma_gemm_kernel).

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
   float2* stat_scratch = reinterpret_cast<float2*>(tmem_slot + 2);  // [4][BN]
   float* bias_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(stat_scratch + 4 * BN) + 15) & ~uintptr_t(15));  // [BN]
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -463,9 +465,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   int cap = sm_count() * CTAS_PER_SM;
   if (cap > p.n_tiles) cap -= cap % p.n_tiles;
   const int grid = p.total_tiles < cap ? p.total_tiles : cap;
-  umma_gemm_kernel<BN, STAGES, OUT_BUFS, CTAS_PER_SM><<<grid, 192, smem, stream>>>(tmA, tmB, tmC, p);
+  const cudaError_t le = launch_pdl(umma_gemm_kernel<BN, STAGES, OUT_BUFS, CTAS_PER_SM>, dim3(grid), dim3(192), smem, stream, tmA, tmB, tmC, p);
   count_launch();
-  return (int)cudaGetLastError();
+  return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
 
 }  // namespace ctu

@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_wgrad_kernel(const __gr
   uint64_t* bar_tempty = bar_tfull + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 1);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_wgrad_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -288,9 +290,9 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmY, WgradPar
   if (items > 0x7fffffffLL) return CTU_E_BADARG;
   p.total_items = (int)items;
   const int grid = p.total_items < slots ? p.total_items : slots;
-  umma_wgrad_kernel<BN, J, SA, SB, CTAS_PER_SM><<<grid, 192, smem, stream>>>(tmX, tmY, p);
+  const cudaError_t le = launch_pdl(umma_wgrad_kernel<BN, J, SA, SB, CTAS_PER_SM>, dim3(grid), dim3(192), smem, stream, tmX, tmY, p);
   count_launch();
-  return (int)cudaGetLastError();
+  return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
 
 }  // namespace ctu

@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) wgrad_halo_kernel(const __gr
   uint64_t* bar_tempty = bars + 3;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) wgrad_halo_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one stage per CTA; several
@@ -266,9 +268,9 @@ static int launch_wh(const CUtensorMap& tmX, const CUtensorMap& tmY, WhParams p,
   p.splits = splits;
   p.total_items = base * splits;
   const int grid = p.total_items < slots ? p.total_items : slots;
-  wgrad_halo_kernel<BN, J, CB, CTAS_PER_SM><<<grid, 192, smem, stream>>>(tmX, tmY, p);
+  const cudaError_t le = launch_pdl(wgrad_halo_kernel<BN, J, CB, CTAS_PER_SM>, dim3(grid), dim3(192), smem, stream, tmX, tmY, p);
   count_launch();
-  return (int)cudaGetLastError();
+  return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
 
 // Returns CTU_E_UNSUPPORTED when the problem does not fit this kernel (the caller then uses umma_wgrad_kernel).

@@ -720,7 +720,8 @@ class Engine:
                 return
             rows = qkv.shape[0]
             dqkv = self._empty(rows, 3 * C)
-            dq = torch.zeros(rows, C, dtype=F32, device=self.dev)
+            direct = dim_head == 32 and n <= 224  # window attention: dQ is written straight into dqkv
+            dq = None if direct else torch.zeros(rows, C, dtype=F32, device=self.dev)
             nwin = windows if mode == 0 else rows // n
             ds = bias_t = None
             if bias_name:
@@ -728,7 +729,8 @@ class Engine:
                 ds = self._empty(nwin, heads, n, n)
             ops.attention_backward(qkv, out, g, lse, dqkv, dq, dim_head=dim_head, n=n, windows=windows, mode=mode,
                                    bias_t=bias_t, ds_out=ds, grid=grid, w=6)
-            ops.cast_f32_bf16(dq, dqkv[:, :C])
+            if dq is not None:
+                ops.cast_f32_bf16(dq, dqkv[:, :C])
             if bias_name:
                 dbt = self.garena.take(heads, n, n)
                 ops.colsum(ds.view(nwin, heads * n * n), dbt.view(-1))

@@ -438,7 +438,8 @@ def patchify_ln_backward(img, pf: int, dtok, dgamma, dbeta, eps: float = 1e-5):
 def attention_backward(qkv, out, dout, lse, dqkv, dq_f32, *, dim_head: int, n: int, windows: int = 0, mode: int = 0,
                        bias_t: Optional[torch.Tensor] = None, ds_out: Optional[torch.Tensor] = None,
                        grid: Tuple[int, int, int, int] = (1, 1, 1, 1), w: int = 6):
-    """Backward of `attention`.  dK/dV -> dqkv[:, C:], dQ accumulated into dq_f32 (fp32 [rows, C], zeroed by the caller)."""
+    """Backward of `attention`.  dK/dV -> dqkv[:, C:], dQ accumulated into dq_f32 (fp32 [rows, C], zeroed by the caller);
+    for dim_head 32 and n <= 224 (the 6^3 windows) dQ goes straight into dqkv[:, :C] and dq_f32 may be None."""
     lib = _lib.require_device()
     C_ = qkv.shape[-1] // 3
     rows = qkv.shape[0]
@@ -449,5 +450,5 @@ def attention_backward(qkv, out, dout, lse, dqkv, dq_f32, *, dim_head: int, n: i
     b, X, Y, Z = grid
     check(lib.ctu_attention_bwd(qkv.data_ptr(), int(qkv.stride(-2)), C_, dim_head, dout.data_ptr(), int(dout.stride(-2)),
                                 lse.data_ptr(), delta.data_ptr(), _ptr(bias_t), dqkv.data_ptr(), int(dqkv.stride(-2)),
-                                dq_f32.data_ptr(), _ptr(ds_out), n, windows, mode, b, X, Y, Z, w, _stream()),
+                                _ptr(dq_f32), _ptr(ds_out), n, windows, mode, b, X, Y, Z, w, _stream()),
           "ctu_attention_bwd")

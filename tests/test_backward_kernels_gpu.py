@@ -330,7 +330,8 @@ def test_attention_backward(mode, D, heads):
     got_lse = lse[t].permute(0, 2, 1)
     assert (got_lse - ref_lse).abs().max().item() < 2e-2
     ref_out.backward(dout.float())
-    assert rel(dq, qr.grad[:, :C]) < 1.5e-2
+    got_dq = dqkv[:, :C] if (D == 32 and n <= 224) else dq   # 6^3 windows: dQ written straight into dqkv
+    assert rel(got_dq, qr.grad[:, :C]) < 1.5e-2
     assert rel(dqkv[:, C:2 * C], qr.grad[:, C:2 * C]) < 1.5e-2
     assert rel(dqkv[:, 2 * C:], qr.grad[:, 2 * C:]) < 1.5e-2
     if bias is not None:

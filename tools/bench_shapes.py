@@ -60,6 +60,15 @@ mk_lin("vit2_ffn_up", 864, 768, 3072, bias=True)
 mk_lin("vit2_ffn_down", 864, 3072, 768, bias=True)
 mk_lin("vit2_out", 864, 768, 768, bias=True)
 mk_lin("vit2_dgrad_qkv", 864, 2304, 768)
+mk_lin("vit2_qkv_bn64", 864, 768, 2304, bn=64)
+mk_lin("vit2_ffn_up_bn64", 864, 768, 3072, bias=True, bn=64)
+mk_lin("vit2_ffn_down_bn64", 864, 3072, 768, bias=True, bn=64)
+mk_lin("vit2_out_bn64", 864, 768, 768, bias=True, bn=64)
+mk_lin("vit2_dgrad_qkv_bn64", 864, 2304, 768, bn=64)
+mk_lin("l3_conv1_512_128", 6912, 512, 128)
+mk_lin("l3_conv1_512_128_bn64", 6912, 512, 128, bn=64)
+mk_lin("l3_conv3_128_512", 6912, 128, 512)
+mk_lin("l3_conv3_128_512_bn64", 6912, 128, 512, bn=64)
 res = {}
 for name, fn, flops, bytes_ in shapes:
     fn(); torch.cuda.synchronize()
