@@ -164,9 +164,10 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    dt = _oracle_train_step_seconds(threads, min(args.warmup, 1), args.steps)
+    wu = min(args.warmup, 1)
+    dt = _oracle_train_step_seconds(threads, wu, args.steps)
     value = 1.0 / dt
-    sample = "1 patch (batch 1) per step: oracle CTUNet fp32 fwd + 5-head Dice-CE + autograd bwd on the host cores (1 warm-up)"
+    sample = f"1 patch (batch 1) per step: oracle CTUNet fp32 fwd + 5-head Dice-CE + autograd bwd on the host cores ({wu} warm-up)"
     print(json.dumps({
         "impl": "reference", "metric": "train_patches_per_s", "value": value, "unit": "patches/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,

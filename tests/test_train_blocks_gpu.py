@@ -81,8 +81,24 @@ def _check(mod, oracle_fn, inputs, tol_grad=TOL_GRAD, skip_params=(), outputs_in
             continue
         assert p.grad is not None, f"{name} received no gradient"
         judge(name, p.grad, ref, sda["b." + name].grad)
+    _dump(mod.__class__.__name__, inputs, report)
     assert not bad, bad
     return report
+
+
+def _dump(name, inputs, report):
+    """Append (ours, bf16-autocast yard-stick) rel-L2 gradient errors to gpurun_out/parity_grads.json (evidence file)."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_grads.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        key = f"{name}{[tuple(x.shape) for x in inputs]}"
+        data[key] = {k: {"ours_vs_fp32": round(v[0], 5), "torch_bf16_autocast_vs_fp32": round(v[1], 5)} for k, v in report.items()}
+        json.dump(data, open(path, "w"), indent=1)
+    except OSError:
+        pass
 
 
 def test_bottleneck_identity_grads():

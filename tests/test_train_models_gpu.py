@@ -133,3 +133,44 @@ def test_graphed_train_step_trains_with_fused_adamw():
     with torch.no_grad():
         after = float(ctunet_loss(model(x), y, loss_func))
     assert abs(after - losses[-1]) < 0.2 and after < eager
+
+
+def test_cunet_training_step():
+    """CUNet (ResNet encoder + transposed-conv / concat decoder, hybrid_CTUNet.py:859-937): 3 deep-supervision heads,
+    gradients finite, loss and head-side gradients match oracle autograd, an optimizer step lowers the loss."""
+    from hybrid_ctunet_b200.losses import DiceCELoss, deep_supervision_targets
+    from hybrid_ctunet_b200.networks.hybrid_CTUNet import CUNet
+    from oracle import ctunet_oracle as O
+    torch.manual_seed(0)
+    model = CUNet(out_channels=14, model_depth=101).cuda().train()
+    lf = DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)
+    torch.manual_seed(1)
+    x = torch.rand(1, 1, 96, 96, 96, device="cuda")
+    y = torch.randint(0, 14, (1, 1, 96, 96, 96), device="cuda").float()
+    t1, t2 = deep_supervision_targets(y)
+
+    def loss_of(lg):
+        return lf(lg[0], y) + 0.5 * (lf(lg[1], t1) + 0.5 * lf(lg[2], t2))
+
+    loss = loss_of(model(x))
+    loss.backward()
+    sd = {k: v.detach().clone().requires_grad_() for k, v in model.state_dict().items()}
+    ref = loss_of(O.cunet_forward(sd, x, 101))
+    ref.backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) < 2e-2 * abs(float(ref.detach()))
+    for n, p in model.named_parameters():
+        if sd[n].grad is None:
+            assert p.grad is None, n
+        else:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    for name in ("res_out.conv.conv.weight", "res_out.conv.conv.bias", "res_out_48x48.conv.conv.weight"):
+        assert _rel(dict(model.named_parameters())[name].grad, sd[name].grad) < 6e-2, name
+    l0 = float(loss.detach())
+    for _ in range(3):
+        opt.step()
+        for p in model.parameters():
+            p.grad = None
+        loss = loss_of(model(x))
+        loss.backward()
+    assert float(loss.detach()) < l0
