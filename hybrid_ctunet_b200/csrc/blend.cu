@@ -66,6 +66,22 @@ __global__ void __launch_bounds__(256) blend_normalize_kernel(const float* __res
   }
 }
 
+// 16-byte vectorised variant: a thread owns four consecutive voxels, loads their counts once and walks the channels
+// (coalesced per channel; the count map is read once instead of C times)
+__global__ void __launch_bounds__(256) blend_normalize_vec_kernel(const float4* __restrict__ acc, const float4* __restrict__ cnt,
+                                                                  float4* __restrict__ out, int C, long long vox4) {
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < vox4; v += (long long)gridDim.x * blockDim.x) {
+    const float4 cn = cnt[v];
+#pragma unroll 2
+    for (int c = 0; c < C; ++c) {
+      const float4 a = acc[(long long)c * vox4 + v];
+      float4 o;
+      o.x = __fdiv_rn(a.x, cn.x); o.y = __fdiv_rn(a.y, cn.y); o.z = __fdiv_rn(a.z, cn.z); o.w = __fdiv_rn(a.w, cn.w);
+      out[(long long)c * vox4 + v] = o;
+    }
+  }
+}
+
 }  // namespace ctu
 
 using namespace ctu;
@@ -114,7 +130,13 @@ extern "C" int ctu_blend_count(const float* imp, float* cnt, int r3, int r2, int
 // out[c][v] = acc[c][v] / cnt[v]  (out may alias acc)
 extern "C" int ctu_blend_normalize(const float* acc, const float* cnt, float* out, int C, long long vox, void* stream) {
   if (!acc || !cnt || !out) return CTU_E_BADARG;
-  blend_normalize_kernel<<<blend_grid((long long)C * vox), 256, 0, (cudaStream_t)stream>>>(acc, cnt, out, C, vox);
+  const bool vec = (vox % 4 == 0) && ((reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(cnt) |
+                                       reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+  if (vec)
+    blend_normalize_vec_kernel<<<blend_grid(vox / 4), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(acc), reinterpret_cast<const float4*>(cnt), reinterpret_cast<float4*>(out), C, vox / 4);
+  else
+    blend_normalize_kernel<<<blend_grid((long long)C * vox), 256, 0, (cudaStream_t)stream>>>(acc, cnt, out, C, vox);
   count_launch();
   return (int)cudaGetLastError();
 }
