@@ -63,14 +63,16 @@ _ITEM_DTYPE = np.dtype([("src", "u8"), ("dst", "u8"), ("kind", "i4"), ("rows", "
 class ItemTable:
     """Device-resident table of ctu_pack_item for the multi-tensor pack / unpack kernels (include/ctunet_b200.h)."""
 
-    def __init__(self, device):
+    def __init__(self, device, unpack: bool = False):
         self.dev = device
-        self.rows: List[tuple] = []          # (src_ptr, dst_ptr, kind, rows, cols, a, b, c, n_elements)
+        self.unpack = unpack
+        self.rows: List[tuple] = []          # (src_ptr, dst_ptr, kind, rows, cols, a, b, c, n_tasks)
         self.table: Optional[torch.Tensor] = None
         self.units = 0
 
-    def add(self, src_ptr, dst_ptr, kind, rows, cols, a, b, c, n_elements) -> int:
-        self.rows.append((int(src_ptr), int(dst_ptr), int(kind), int(rows), int(cols), int(a), int(b), int(c), int(n_elements)))
+    def add(self, src_ptr, dst_ptr, kind, rows, cols, a, b, c) -> int:
+        n_tasks = int(ops._lib.load().ctu_pack_item_tasks(int(self.unpack), int(kind), int(rows), int(cols), int(a), int(b), int(c)))
+        self.rows.append((int(src_ptr), int(dst_ptr), int(kind), int(rows), int(cols), int(a), int(b), int(c), n_tasks))
         self.table = None
         return len(self.rows) - 1
 
@@ -153,7 +155,7 @@ class WeightCache:
             if bias_name:
                 bias = ps[1].detach().to(F32).contiguous() if bias_repeat == 1 else ps[1].detach().to(F32).repeat(bias_repeat)
             pw = PackedWeight(buf, n, a_c if a_c is not None else k_pad // (ksize ** 3), ksize, bn, convt, bias)
-            idx = self.items.add(w.data_ptr(), buf.data_ptr(), kind, n_pad, k_pad, a, b, c, n_pad * k_pad)
+            idx = self.items.add(w.data_ptr(), buf.data_ptr(), kind, n_pad, k_pad, a, b, c)
         if bias_name and bias_repeat != 1:
             pw.bias.copy_(ps[1].detach().to(F32).repeat(bias_repeat))
         self.items.run("ctu_pack_weights", only=idx)
@@ -553,12 +555,12 @@ class Engine:
         if getattr(self, "_gsig", None) != sig:
             total = sum(P(pn).numel() for pn, _, _, _ in recs)
             self._gflat = torch.empty(total, dtype=F32, device=self.dev)
-            self._gtable = ItemTable(self.dev)
+            self._gtable = ItemTable(self.dev, unpack=True)
             self._gviews = []
             off = 0
             for pn, buf, ld, (code, a_, b_, c_) in recs:
                 n = P(pn).numel()
-                self._gtable.add(buf.data_ptr(), self._gflat.data_ptr() + 4 * off, code, n, ld, a_, b_, c_, n)
+                self._gtable.add(buf.data_ptr(), self._gflat.data_ptr() + 4 * off, code, n, ld, a_, b_, c_)
                 self._gviews.append((pn, off, n))
                 off += n
             self._gsig = sig

@@ -83,6 +83,8 @@ def _declare(lib):
     lib.ctu_umma_gemm.restype = C.c_int
     lib.ctu_umma_wgrad.argtypes = [C.POINTER(WgradDesc), C.c_void_p]
     lib.ctu_umma_wgrad.restype = C.c_int
+    lib.ctu_pack_item_tasks.argtypes = [C.c_int] * 7
+    lib.ctu_pack_item_tasks.restype = C.c_longlong
     lib.ctu_launch_count.argtypes = []
     lib.ctu_launch_count.restype = C.c_int64
     lib.ctu_device_ok.argtypes = []

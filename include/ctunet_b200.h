@@ -250,7 +250,8 @@ int ctu_ensemble_argmax(const float* p1, const float* p2, int C, long long V, ui
  * ctu_unpack_grads : dst = fp32 gradient in the parameter's own layout (rows = its element count), src = fp32
  *   accumulator written by ctu_umma_wgrad / ctu_colsum with row pitch cols; kinds LIN, CONV3 (c = cip), CONVT, PS,
  *   PS_BIAS (a = co, c = k^3), CIN1, VEC.
- * unit0 = index of the item's first work unit (256 elements per unit); items sorted by unit0. */
+ * A thread-task moves the innermost run of the item's index map (ctu_pack_item_tasks gives the task count of an item);
+ * unit0 = index of the item's first work unit (256 tasks per unit); items sorted by unit0. */
 #define CTU_PACK_LIN 0
 #define CTU_PACK_LIN_T 1
 #define CTU_PACK_CONV3 2
@@ -270,6 +271,7 @@ typedef struct ctu_pack_item {
   int32_t a, b, c;
   int64_t unit0;
 } ctu_pack_item;
+long long ctu_pack_item_tasks(int unpack, int kind, int rows, int cols, int a, int b, int c);
 int ctu_pack_weights(const ctu_pack_item* items_dev, int n_items, long long total_units, void* stream);
 int ctu_unpack_grads(const ctu_pack_item* items_dev, int n_items, long long total_units, void* stream);
 
