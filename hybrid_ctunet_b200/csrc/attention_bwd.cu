@@ -4,9 +4,10 @@
 // shared memory, recomputing P^T = exp2(S^T - lse) from the log-sum-exp the forward saved:
 //   dV  += P^T dO            dP^T = V dO^T          dS^T = P^T o (dP^T - delta),  delta = rowsum(dO o O)
 //   dK  += dS^T Q * scale    dQ   += dS K * scale   dBias = dS (summed over windows by ctu_colsum afterwards)
-// dK / dV rows are owned by exactly one warp and written as bf16; dQ gets contributions from every key block,
-// so it is reduced across the CTA's warps in shared memory (shared atomics) and added to an fp32 buffer with
-// vector reductions.
+// dK / dV rows are owned by exactly one warp and written as bf16; dQ gets contributions from every key, so the
+// warps park dS of the chunk in shared memory as one [query][key] tile and the dQ product over the CTA's whole key
+// range is split by OUTPUT tile over the warps (no shared-memory atomics: fp32 shared atomics are CAS loops).  When
+// the CTA does not hold every key, its partial dQ is added to an fp32 buffer with vector reductions.
 #include "attention_common.cuh"
 #include "../../include/ctunet_b200.h"
 #include "host_util.h"
@@ -51,15 +52,14 @@ __global__ void __launch_bounds__(32 * NW) attention_bwd_kernel(const __nv_bfloa
                                                             float* __restrict__ dq_f32, __nv_bfloat16* __restrict__ ds_out,
                                                             int n, TokenMap map) {
   constexpr int LDQ = D + 8;
-  constexpr int LDK = 16 + 8;
   __shared__ __align__(16) __nv_bfloat16 Qs[QC * LDQ];
   __shared__ __align__(16) __nv_bfloat16 dOs[QC * LDQ];
   __shared__ __align__(16) __nv_bfloat16 Qt[D * LDT];
   __shared__ __align__(16) __nv_bfloat16 dOt[D * LDT];
   constexpr int NT = 32 * NW;  // threads per CTA: NW warps, 16 keys each
-  __shared__ __align__(16) __nv_bfloat16 Ktw[NW][D * LDK];
-  __shared__ __align__(16) __nv_bfloat16 patch[NW][16 * LDK];
-  __shared__ __align__(16) float dQs[QC * D];
+  constexpr int LDS = NW * 16 + 8;  // pitch of the key-contiguous buffers (LDS/2 = 4 mod 8: conflict-free fragments)
+  __shared__ __align__(16) __nv_bfloat16 Kt[D * LDS];    // K^T of the CTA's keys: [d][key]
+  __shared__ __align__(16) __nv_bfloat16 dSs[QC * LDS];  // dS of the current chunk: [query][key]
   __shared__ float lse_s[QC], delta_s[QC];
   __shared__ long long qrow_s[QC];
 
@@ -89,16 +89,13 @@ __global__ void __launch_bounds__(32 * NW) attention_bwd_kernel(const __nv_bfloa
     vf[kk][2] = va ? *reinterpret_cast<const uint32_t*>(qkv + ra * ld_qkv + 2 * C + c + 8) : 0u;
     vf[kk][3] = vb ? *reinterpret_cast<const uint32_t*>(qkv + rb * ld_qkv + 2 * C + c + 8) : 0u;
   }
-  {
-    __nv_bfloat16* kt = Ktw[warp];
-    for (int i = lane; i < 16 * (D / 8); i += 32) {
-      const int j = i / (D / 8), vi = i % (D / 8);
-      uint4 kv = make_uint4(0, 0, 0, 0);
-      if (key0 + j < n) kv = *reinterpret_cast<const uint4*>(qkv + token_row(map, win, key0 + j, n) * ld_qkv + C + h * D + vi * 8);
-      const __nv_bfloat16* ke = reinterpret_cast<const __nv_bfloat16*>(&kv);
+  for (int i = lane; i < 16 * (D / 8); i += 32) {
+    const int j = i / (D / 8), vi = i % (D / 8);
+    uint4 kv = make_uint4(0, 0, 0, 0);
+    if (key0 + j < n) kv = *reinterpret_cast<const uint4*>(qkv + token_row(map, win, key0 + j, n) * ld_qkv + C + h * D + vi * 8);
+    const __nv_bfloat16* ke = reinterpret_cast<const __nv_bfloat16*>(&kv);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) kt[(vi * 8 + e) * LDK + j] = ke[e];
-    }
+    for (int e = 0; e < 8; ++e) Kt[(vi * 8 + e) * LDS + warp * 16 + j] = ke[e];
   }
 
   float dk[D / 8][4], dv[D / 8][4];
@@ -124,7 +121,6 @@ __global__ void __launch_bounds__(32 * NW) attention_bwd_kernel(const __nv_bfloa
       delta_s[tid] = ok ? delta[row * heads + h] : 0.f;
     }
     __syncthreads();
-    for (int i = tid; i < QC * D / 4; i += NT) *reinterpret_cast<float4*>(dQs + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = tid; i < QC * (D / 8); i += NT) {
       const int j = i / (D / 8), vi = i % (D / 8);
       const long long row = qrow_s[j];
@@ -202,60 +198,61 @@ __global__ void __launch_bounds__(32 * NW) attention_bwd_kernel(const __nv_bfloa
         mma_bf16_16816(dk[dn], dsA[kt], *reinterpret_cast<const uint32_t*>(qp), *reinterpret_cast<const uint32_t*>(qp + 8));
       }
     }
-    // ---- dQ partial of this warp: (16 queries x 16 keys) . (16 keys x D), two 16-query tiles
-    __nv_bfloat16* pp = patch[warp];
-    const __nv_bfloat16* kt_s = Ktw[warp];
+    // ---- dS of this warp's 16 keys into the CTA-wide [query][key] tile
 #pragma unroll
-    for (int mt = 0; mt < QC / 16; ++mt) {
-      __syncwarp();
-      // transpose through the per-warp patch: patch[query][key]
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const uint32_t u01 = dsA[mt][half * 2 + 0], u23 = dsA[mt][half * 2 + 1];
-        const __nv_bfloat162 v01 = *reinterpret_cast<const __nv_bfloat162*>(&u01);
-        const __nv_bfloat162 v23 = *reinterpret_cast<const __nv_bfloat162*>(&u23);
-        const int qa = half * 8 + 2 * t;
-        pp[qa * LDK + g] = v01.x;
-        pp[(qa + 1) * LDK + g] = v01.y;
-        pp[qa * LDK + g + 8] = v23.x;
-        pp[(qa + 1) * LDK + g + 8] = v23.y;
-      }
-      __syncwarp();
-      uint32_t af[4];
-      af[0] = *reinterpret_cast<const uint32_t*>(pp + g * LDK + 2 * t);
-      af[1] = *reinterpret_cast<const uint32_t*>(pp + (g + 8) * LDK + 2 * t);
-      af[2] = *reinterpret_cast<const uint32_t*>(pp + g * LDK + 2 * t + 8);
-      af[3] = *reinterpret_cast<const uint32_t*>(pp + (g + 8) * LDK + 2 * t + 8);
-      float* dqw = dQs + (mt * 16) * D;
-#pragma unroll
-      for (int dn = 0; dn < D / 8; ++dn) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        const __nv_bfloat16* bp = kt_s + (dn * 8 + g) * LDK + 2 * t;
-        mma_bf16_16816(acc, af, *reinterpret_cast<const uint32_t*>(bp), *reinterpret_cast<const uint32_t*>(bp + 8));
-        atomicAdd(dqw + g * D + dn * 8 + 2 * t, acc[0]);
-        atomicAdd(dqw + g * D + dn * 8 + 2 * t + 1, acc[1]);
-        atomicAdd(dqw + (g + 8) * D + dn * 8 + 2 * t, acc[2]);
-        atomicAdd(dqw + (g + 8) * D + dn * 8 + 2 * t + 1, acc[3]);
-      }
+    for (int qs = 0; qs < QC / 8; ++qs) {
+      const uint32_t u01 = dsA[qs >> 1][(qs & 1) * 2 + 0], u23 = dsA[qs >> 1][(qs & 1) * 2 + 1];
+      const __nv_bfloat162 v01 = *reinterpret_cast<const __nv_bfloat162*>(&u01);
+      const __nv_bfloat162 v23 = *reinterpret_cast<const __nv_bfloat162*>(&u23);
+      __nv_bfloat16* dp_ = dSs + (qs * 8 + 2 * t) * LDS + warp * 16 + g;
+      dp_[0] = v01.x;
+      dp_[LDS] = v01.y;
+      dp_[8] = v23.x;
+      dp_[LDS + 8] = v23.y;
     }
     __syncthreads();
-    // ---- dQ of this chunk, summed over the CTA's warps in dQs: the whole key range lives in this CTA (DIRECT_DQ) ->
-    // final value, written as bf16; otherwise a partial sum added to the fp32 dQ buffer with vector reductions
-    for (int i = tid; i < QC * (D / 4); i += NT) {
-      const int j = i / (D / 4), c4 = (i % (D / 4)) * 4;
-      const long long row = qrow_s[j];
-      if (row < 0) continue;
-      const float4 a = *reinterpret_cast<const float4*>(dQs + j * D + c4);
-      if constexpr (DIRECT_DQ) {
-        uint2 pk;
-        pk.x = pack_bf16x2(a.x * scale, a.y * scale);
-        pk.y = pack_bf16x2(a.z * scale, a.w * scale);
-        *reinterpret_cast<uint2*>(dqkv + row * ld_dqkv + h * D + c4) = pk;
-      } else {
-        float* dst = dq_f32 + row * C + h * D + c4;
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x * scale), "f"(a.y * scale),
-                     "f"(a.z * scale), "f"(a.w * scale)
-                     : "memory");
+    // ---- dQ of this chunk = dS (32 x keys) . K (keys x D): 2 x D/8 output tiles of 16 x 8 spread over the warps, the
+    // whole key range of the CTA contracted by each (no cross-warp reduction).  With every key of the (window, head) in
+    // this CTA (DIRECT_DQ) that is the final value, written as bf16; otherwise a partial sum added to the fp32 buffer.
+    {
+      constexpr int TILES = 2 * (D / 8);
+      constexpr int TPW = TILES / NW > 0 ? TILES / NW : 1;  // tiles per warp (all in one 16-query row block)
+      const int tile0 = warp * TPW;
+      if (tile0 < TILES) {
+        const int mt = tile0 / (D / 8), dn0 = tile0 % (D / 8);
+        float acc[TPW][4];
+#pragma unroll
+        for (int i = 0; i < TPW; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        const __nv_bfloat16* ap = dSs + (mt * 16 + g) * LDS + 2 * t;
+#pragma unroll
+        for (int ks = 0; ks < NW; ++ks) {
+          uint32_t af[4];
+          af[0] = *reinterpret_cast<const uint32_t*>(ap + ks * 16);
+          af[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * LDS + ks * 16);
+          af[2] = *reinterpret_cast<const uint32_t*>(ap + ks * 16 + 8);
+          af[3] = *reinterpret_cast<const uint32_t*>(ap + 8 * LDS + ks * 16 + 8);
+#pragma unroll
+          for (int i = 0; i < TPW; ++i) {
+            const __nv_bfloat16* bp = Kt + ((dn0 + i) * 8 + g) * LDS + ks * 16 + 2 * t;
+            mma_bf16_16816(acc[i], af, *reinterpret_cast<const uint32_t*>(bp), *reinterpret_cast<const uint32_t*>(bp + 8));
+          }
+        }
+        const long long row_a = qrow_s[mt * 16 + g], row_b = qrow_s[mt * 16 + g + 8];
+#pragma unroll
+        for (int i = 0; i < TPW; ++i) {
+          const int c = h * D + (dn0 + i) * 8 + 2 * t;
+          if constexpr (DIRECT_DQ) {
+            if (row_a >= 0) *reinterpret_cast<uint32_t*>(dqkv + row_a * ld_dqkv + c) = pack_bf16x2(acc[i][0] * scale, acc[i][1] * scale);
+            if (row_b >= 0) *reinterpret_cast<uint32_t*>(dqkv + row_b * ld_dqkv + c) = pack_bf16x2(acc[i][2] * scale, acc[i][3] * scale);
+          } else {
+            if (row_a >= 0)
+              asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dq_f32 + row_a * C + c), "f"(acc[i][0] * scale),
+                           "f"(acc[i][1] * scale) : "memory");
+            if (row_b >= 0)
+              asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(dq_f32 + row_b * C + c), "f"(acc[i][2] * scale),
+                           "f"(acc[i][3] * scale) : "memory");
+          }
+        }
       }
     }
   }

@@ -47,20 +47,35 @@ __device__ __forceinline__ void st8f(float* p, const float (&f)[8]) {
   *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
 }
 
-__device__ __forceinline__ void in_coeffs_bw(const double* st, double inv_n, float eps, float& scale, float& shift) {
+__device__ __forceinline__ void in_coeffs_d(const double* st, double inv_n, float eps, double& rstd, double& shift) {
   const double mean = st[0] * inv_n;
   double var = st[1] * inv_n - mean * mean;
   var = var < 0.0 ? 0.0 : var;
-  const double rstd = rsqrt(var + (double)eps);
-  scale = (float)rstd;
-  shift = (float)(-mean * rstd);
+  rstd = rsqrt(var + (double)eps);
+  shift = -mean * rstd;
 }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
 
 // ------------------------------------------------------------------------------------------------
 // Backward of  out = act( IN(x) [+ r | + IN(r)] )  (forward: in_apply_kernel).  With g = dout * act'(out):
 //   dx = rstd_x * (g - mean(g) - xhat * mean(g * xhat)),   dr = g   or the same formula with r's statistics.
 // Pass 1 accumulates the per-(instance, channel) sums (fp64 atomics), pass 2 applies them.
-template <int RES>
+//
+// Both passes: a thread owns 8 channels of a row (16-byte vectors, a warp covers 512 contiguous bytes) and walks rows
+// with a grid stride, UNR rows per iteration with every load issued before the first use.  Per-channel coefficients
+// are computed ONCE per block (one fp64 rsqrt per channel, spread over the threads) and staged in shared memory.
+// `rev` walks the instance from its last row to its first: pass 1 runs right after the kernel that produced dout
+// front to back, so the tail of dout is what the L2 still holds; pass 2 then walks forward over what pass 1 read last.
+
+template <int RES, bool HASX, int IN_UNR>
 __global__ void __launch_bounds__(256) in_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dout, int ldd,
                                                            const __nv_bfloat16* __restrict__ out, int ldo,
                                                            const __nv_bfloat16* __restrict__ x, int ldx,
@@ -68,8 +83,8 @@ __global__ void __launch_bounds__(256) in_bwd_stats_kernel(const __nv_bfloat16* 
                                                            const __nv_bfloat16* __restrict__ res, int ldr,
                                                            const double* __restrict__ rstats, int rs_ld, long long S,
                                                            int C, float eps, int act, float slope,
-                                                           double* __restrict__ sums) {
-  __shared__ float red[3][256][8];
+                                                           double* __restrict__ sums, int rev) {
+  extern __shared__ __align__(16) float in_sm[];  // coefficients [4][C] first, then the block reduction [3][256][8]
   const int tpr = C / 8;
   const int rpb = 256 / tpr;
   const int cv = threadIdx.x % tpr;
@@ -77,65 +92,85 @@ __global__ void __launch_bounds__(256) in_bwd_stats_kernel(const __nv_bfloat16* 
   const int b = blockIdx.y;
   const double inv_n = 1.0 / (double)S;
   const float inv_slope = 1.f / slope;
+  constexpr bool has_x = HASX;
+  if (has_x || RES == 2) {
+    for (int c = threadIdx.x; c < C; c += 256) {
+      double r_, s_;
+      if (has_x) {
+        in_coeffs_d(xstats + ((long long)b * xs_ld + c) * 2, inv_n, eps, r_, s_);
+        in_sm[c] = (float)r_; in_sm[C + c] = (float)s_;
+      }
+      if (RES == 2) {
+        in_coeffs_d(rstats + ((long long)b * rs_ld + c) * 2, inv_n, eps, r_, s_);
+        in_sm[2 * C + c] = (float)r_; in_sm[3 * C + c] = (float)s_;
+      }
+    }
+    __syncthreads();
+  }
+  float sc[8], sh[8], rsc[8], rsh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = has_x ? in_sm[cv * 8 + j] : 0.f;
+    sh[j] = has_x ? in_sm[C + cv * 8 + j] : 0.f;
+    rsc[j] = RES == 2 ? in_sm[2 * C + cv * 8 + j] : 0.f;
+    rsh[j] = RES == 2 ? in_sm[3 * C + cv * 8 + j] : 0.f;
+  }
   float sg[8], sgx[8], sgr[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sg[j] = sgx[j] = sgr[j] = 0.f;
-  if (rl < rpb) {
-    float sc[8], sh[8], rsc[8], rsh[8];
+  const long long base = (long long)b * S;
+  const long long stride = (long long)gridDim.x * rpb;
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  for (long long r0 = (long long)blockIdx.x * rpb + rl; r0 < S; r0 += stride * IN_UNR) {
+    uint4 gq[IN_UNR], oq[IN_UNR], xq[IN_UNR], rq[IN_UNR];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      in_coeffs_bw(xstats + ((long long)b * xs_ld + cv * 8 + j) * 2, inv_n, eps, sc[j], sh[j]);
-      if (RES == 2) in_coeffs_bw(rstats + ((long long)b * rs_ld + cv * 8 + j) * 2, inv_n, eps, rsc[j], rsh[j]);
+    for (int u = 0; u < IN_UNR; ++u) {
+      const long long r = r0 + u * stride;
+      const bool ok = r < S;
+      const long long row = base + (rev ? S - 1 - r : r);
+      gq[u] = ok ? ldg16(dout + row * ldd + cv * 8) : z4;
+      oq[u] = (ok && act) ? ldg16(out + row * ldo + cv * 8) : z4;
+      xq[u] = (ok && has_x) ? ldg16(x + row * ldx + cv * 8) : z4;
+      if (RES == 2) rq[u] = ok ? ldg16(res + row * ldr + cv * 8) : z4;
     }
-    const long long base = (long long)b * S;
-    for (long long r = (long long)blockIdx.x * rpb + rl; r < S; r += (long long)gridDim.x * rpb) {
+#pragma unroll
+    for (int u = 0; u < IN_UNR; ++u) {
       float g[8], o[8], xv[8], rv[8];
-      ld8(dout + (base + r) * ldd + cv * 8, g);
-      if (act) ld8(out + (base + r) * ldo + cv * 8, o);
-      if (x != nullptr) ld8(x + (base + r) * ldx + cv * 8, xv);
-      if (RES == 2) ld8(res + (base + r) * ldr + cv * 8, rv);
+      unpack8(gq[u], g); unpack8(oq[u], o); unpack8(xq[u], xv);
+      if (RES == 2) unpack8(rq[u], rv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float gj = g[j];
         if (act) gj = o[j] > 0.f ? gj : gj * slope;
         sg[j] += gj;
         // without a residual the normalised value is recovered from the output: xhat = lrelu^-1(out)
-        const float xh = x != nullptr ? fmaf(xv[j], sc[j], sh[j]) : (o[j] > 0.f ? o[j] : o[j] * inv_slope);
+        const float xh = has_x ? fmaf(xv[j], sc[j], sh[j]) : (o[j] > 0.f ? o[j] : o[j] * inv_slope);
         sgx[j] += gj * xh;
         if (RES == 2) sgr[j] += gj * fmaf(rv[j], rsc[j], rsh[j]);
       }
     }
   }
+  // block reduction over the rpb row slots: one output (array, channel) per thread, then ONE fp64 atomic each
+  __syncthreads();  // everyone is done with the coefficient table
+  float* red = in_sm;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    red[0][threadIdx.x][j] = sg[j];
-    red[1][threadIdx.x][j] = sgx[j];
-    red[2][threadIdx.x][j] = sgr[j];
+    red[(0 * 256 + threadIdx.x) * 8 + j] = sg[j];
+    red[(1 * 256 + threadIdx.x) * 8 + j] = sgx[j];
+    if (RES == 2) red[(2 * 256 + threadIdx.x) * 8 + j] = sgr[j];
   }
   __syncthreads();
-  if (rl == 0) {
-    double a0[8], a1[8], a2[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { a0[j] = 0; a1[j] = 0; a2[j] = 0; }
-    for (int i = 0; i < rpb; ++i) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a0[j] += red[0][i * tpr + cv][j];
-        a1[j] += red[1][i * tpr + cv][j];
-        a2[j] += red[2][i * tpr + cv][j];
-      }
-    }
-    double* dst = sums + ((long long)b * C + cv * 8) * 4;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(dst + 4 * j, a0[j]);
-      atomicAdd(dst + 4 * j + 1, a1[j]);
-      if (RES == 2) atomicAdd(dst + 4 * j + 2, a2[j]);
-    }
+  constexpr int NA = RES == 2 ? 3 : 2;
+  for (int o = threadIdx.x; o < NA * C; o += 256) {
+    const int a = o / C, c = o - a * C;
+    const float* rp = red + (a * 256 + (c >> 3)) * 8 + (c & 7);
+    float acc = 0.f;
+    for (int i = 0; i < rpb; ++i) acc += rp[i * tpr * 8];
+    atomicAdd(sums + ((long long)b * C + c) * 4 + a, (double)acc);
   }
 }
 
-template <int RES>
+template <int RES, bool HASX, int IN_UNR>
 __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, int ldd,
                                                            const __nv_bfloat16* __restrict__ out, int ldo,
                                                            const __nv_bfloat16* __restrict__ x, int ldx,
@@ -145,46 +180,74 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const __nv_bfloat16* 
                                                            int C, float eps, int act, float slope,
                                                            const double* __restrict__ sums,
                                                            __nv_bfloat16* __restrict__ dx, int lddx,
-                                                           __nv_bfloat16* __restrict__ dres, int lddr) {
+                                                           __nv_bfloat16* __restrict__ dres, int lddr, int rev) {
+  // dx = A g + B v + K with v = x (or xhat recovered from the output when x is not kept); likewise dr for RES == 2
+  extern __shared__ __align__(16) float in_sm[];  // [6][C]
   const int tpr = C / 8;
   const int rpb = 256 / tpr;
   const int cv = threadIdx.x % tpr;
   const int rl = threadIdx.x / tpr;
-  if (rl >= rpb) return;
   const int b = blockIdx.y;
   const double inv_n = 1.0 / (double)S;
-  float sc[8], sh[8], rsc[8], rsh[8], mg[8], mgx[8], mgr[8];
+  constexpr bool has_x = HASX;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    double r_, s_;
+    in_coeffs_d(xstats + ((long long)b * xs_ld + c) * 2, inv_n, eps, r_, s_);
+    const double* sp = sums + ((long long)b * C + c) * 4;
+    const double mg = sp[0] * inv_n, mgx = sp[1] * inv_n;
+    in_sm[c] = (float)r_;
+    in_sm[C + c] = (float)(has_x ? -r_ * r_ * mgx : -r_ * mgx);
+    in_sm[2 * C + c] = (float)(has_x ? -r_ * mg - s_ * r_ * mgx : -r_ * mg);
+    if (RES == 2) {
+      const double mgr = sp[2] * inv_n;
+      in_coeffs_d(rstats + ((long long)b * rs_ld + c) * 2, inv_n, eps, r_, s_);
+      in_sm[3 * C + c] = (float)r_;
+      in_sm[4 * C + c] = (float)(-r_ * r_ * mgr);
+      in_sm[5 * C + c] = (float)(-r_ * mg - s_ * r_ * mgr);
+    }
+  }
+  __syncthreads();
+  float cA[8], cB[8], cK[8], rA[8], rB[8], rK[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    in_coeffs_bw(xstats + ((long long)b * xs_ld + cv * 8 + j) * 2, inv_n, eps, sc[j], sh[j]);
-    if (RES == 2) in_coeffs_bw(rstats + ((long long)b * rs_ld + cv * 8 + j) * 2, inv_n, eps, rsc[j], rsh[j]);
-    const double* sp = sums + ((long long)b * C + cv * 8 + j) * 4;
-    mg[j] = (float)(sp[0] * inv_n);
-    mgx[j] = (float)(sp[1] * inv_n);
-    mgr[j] = RES == 2 ? (float)(sp[2] * inv_n) : 0.f;
+    cA[j] = in_sm[cv * 8 + j]; cB[j] = in_sm[C + cv * 8 + j]; cK[j] = in_sm[2 * C + cv * 8 + j];
+    if (RES == 2) { rA[j] = in_sm[3 * C + cv * 8 + j]; rB[j] = in_sm[4 * C + cv * 8 + j]; rK[j] = in_sm[5 * C + cv * 8 + j]; }
   }
   const long long base = (long long)b * S;
   const float inv_slope = 1.f / slope;
-  for (long long r = (long long)blockIdx.x * rpb + rl; r < S; r += (long long)gridDim.x * rpb) {
-    float g[8], o[8], xv[8], rv[8], ox[8], orr[8];
-    ld8(dout + (base + r) * ldd + cv * 8, g);
-    if (act) ld8(out + (base + r) * ldo + cv * 8, o);
-    if (x != nullptr) ld8(x + (base + r) * ldx + cv * 8, xv);
-    if (RES == 2) ld8(res + (base + r) * ldr + cv * 8, rv);
+  const long long stride = (long long)gridDim.x * rpb;
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  for (long long r0 = (long long)blockIdx.x * rpb + rl; r0 < S; r0 += stride * IN_UNR) {
+    uint4 gq[IN_UNR], oq[IN_UNR], xq[IN_UNR], rq[IN_UNR];
+    long long rows[IN_UNR];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float gj = g[j];
-      if (act) gj = o[j] > 0.f ? gj : gj * slope;
-      const float xh = x != nullptr ? fmaf(xv[j], sc[j], sh[j]) : (o[j] > 0.f ? o[j] : o[j] * inv_slope);
-      ox[j] = sc[j] * (gj - mg[j] - xh * mgx[j]);
-      if (RES == 1) orr[j] = gj;
-      if (RES == 2) {
-        const float rh = fmaf(rv[j], rsc[j], rsh[j]);
-        orr[j] = rsc[j] * (gj - mg[j] - rh * mgr[j]);
-      }
+    for (int u = 0; u < IN_UNR; ++u) {
+      const long long r = r0 + u * stride;
+      const bool ok = r < S;
+      rows[u] = ok ? base + (rev ? S - 1 - r : r) : -1;
+      gq[u] = ok ? ldg16(dout + rows[u] * ldd + cv * 8) : z4;
+      oq[u] = (ok && act) ? ldg16(out + rows[u] * ldo + cv * 8) : z4;
+      xq[u] = (ok && has_x) ? ldg16(x + rows[u] * ldx + cv * 8) : z4;
+      if (RES == 2) rq[u] = ok ? ldg16(res + rows[u] * ldr + cv * 8) : z4;
     }
-    st8(dx + (base + r) * lddx + cv * 8, ox);
-    if (RES) st8(dres + (base + r) * lddr + cv * 8, orr);
+#pragma unroll
+    for (int u = 0; u < IN_UNR; ++u) {
+      if (rows[u] < 0) continue;
+      float g[8], o[8], xv[8], rv[8], ox[8], orr[8];
+      unpack8(gq[u], g); unpack8(oq[u], o); unpack8(xq[u], xv);
+      if (RES == 2) unpack8(rq[u], rv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float gj = g[j];
+        if (act) gj = o[j] > 0.f ? gj : gj * slope;
+        const float v = has_x ? xv[j] : (o[j] > 0.f ? o[j] : o[j] * inv_slope);
+        ox[j] = fmaf(gj, cA[j], fmaf(v, cB[j], cK[j]));
+        if (RES == 1) orr[j] = gj;
+        if (RES == 2) orr[j] = fmaf(gj, rA[j], fmaf(rv[j], rB[j], rK[j]));
+      }
+      st8(dx + rows[u] * lddx + cv * 8, ox);
+      if (RES) st8(dres + rows[u] * lddr + cv * 8, orr);
+    }
   }
 }
 
@@ -709,12 +772,22 @@ extern "C" int ctu_in_bwd_stats(const void* dout, int ldd, const void* out, int 
   dim3 grid;
   in_grid(S, C, B, 16, grid);
   cudaStream_t st = (cudaStream_t)stream;
-  if (rstats)
-    in_bwd_stats_kernel<2><<<grid, 256, 0, st>>>((const bf16*)dout, ldd, (const bf16*)out, ldo, (const bf16*)x, ldx, xstats,
-                                                 xs_ld, (const bf16*)res, ldr, rstats, rs_ld, S, C, eps, act, slope, sums);
-  else
-    in_bwd_stats_kernel<0><<<grid, 256, 0, st>>>((const bf16*)dout, ldd, (const bf16*)out, ldo, (const bf16*)x, ldx, xstats,
-                                                 xs_ld, nullptr, 0, nullptr, 0, S, C, eps, act, slope, sums);
+  const size_t red_bytes = (size_t)(rstats ? 3 : 2) * 256 * 8 * sizeof(float);
+  const size_t coef_bytes = (size_t)4 * C * sizeof(float);
+  const size_t smem = red_bytes > coef_bytes ? red_bytes : coef_bytes;
+#define CTU_INS(R, HX, U)                                                                                              \
+  in_bwd_stats_kernel<R, HX, U><<<grid, 256, smem, st>>>((const bf16*)dout, ldd, (const bf16*)out, ldo, (const bf16*)x,  \
+                                                         ldx, xstats, xs_ld, (const bf16*)(R == 2 ? res : nullptr), ldr, \
+                                                         R == 2 ? rstats : nullptr, rs_ld, S, C, eps, act, slope, sums, 1)
+  if (rstats) {
+    if (!x) return CTU_E_BADARG;
+    CTU_INS(2, true, 2);
+  } else if (x) {
+    CTU_INS(0, true, 2);
+  } else {
+    CTU_INS(0, false, 4);
+  }
+#undef CTU_INS
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -728,16 +801,19 @@ extern "C" int ctu_in_bwd_apply(const void* dout, int ldd, const void* out, int 
   if (ldd % 8 || (x && ldx % 8) || lddx % 8 || (act && ldo % 8)) return CTU_E_BADARG;
   if (res_mode < 0 || res_mode > 2 || (res_mode && (!dres || lddr % 8)) || (res_mode == 2 && (!res || !rstats || ldr % 8)))
     return CTU_E_BADARG;
+  if (res_mode && !x) return CTU_E_BADARG;
   dim3 grid;
-  in_grid(S, C, B, 4, grid);
+  in_grid(S, C, B, 8, grid);
   cudaStream_t st = (cudaStream_t)stream;
-#define CTU_INB(R)                                                                                                    \
-  in_bwd_apply_kernel<R><<<grid, 256, 0, st>>>((const bf16*)dout, ldd, (const bf16*)out, ldo, (const bf16*)x, ldx,    \
-                                               xstats, xs_ld, (const bf16*)res, ldr, rstats, rs_ld, S, C, eps, act,  \
-                                               slope, sums, (bf16*)dx, lddx, (bf16*)dres, lddr)
-  if (res_mode == 0) CTU_INB(0);
-  else if (res_mode == 1) CTU_INB(1);
-  else CTU_INB(2);
+  const size_t smem = (size_t)(res_mode == 2 ? 6 : 3) * C * sizeof(float);
+#define CTU_INB(R, HX, U)                                                                                              \
+  in_bwd_apply_kernel<R, HX, U><<<grid, 256, smem, st>>>((const bf16*)dout, ldd, (const bf16*)out, ldo, (const bf16*)x,  \
+                                                         ldx, xstats, xs_ld, (const bf16*)res, ldr, rstats, rs_ld, S, C, \
+                                                         eps, act, slope, sums, (bf16*)dx, lddx, (bf16*)dres, lddr, 0)
+  if (res_mode == 0 && !x) CTU_INB(0, false, 4);
+  else if (res_mode == 0) CTU_INB(0, true, 2);
+  else if (res_mode == 1) CTU_INB(1, true, 2);
+  else CTU_INB(2, true, 2);
 #undef CTU_INB
   count_launch();
   return (int)cudaGetLastError();

@@ -25,6 +25,13 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
   t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
   t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
 }
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) =
       make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
@@ -80,43 +87,67 @@ __device__ __forceinline__ void in_coeffs(const double* st, double inv_n, float 
   shift = (float)(-mean * rstd);
 }
 
-template <int RES>  // 0 none, 1 raw residual, 2 normalised residual
+// A thread owns 8 channels of a row and walks rows with a grid stride, IN_UNR rows per iteration with every load issued
+// before the first use; the per-channel (scale, shift) pairs are computed once per block (one fp64 rsqrt per channel,
+// spread over the threads) and staged in shared memory.  `rev` walks each instance from its last row to its first:
+// the kernel runs right after the GEMM that wrote x front to back, so the tail of x is what the L2 still holds.
+template <int RES, int IN_UNR>  // RES: 0 none, 1 raw residual, 2 normalised residual
 __global__ void __launch_bounds__(256) in_apply_kernel(const __nv_bfloat16* __restrict__ x, int ldx,
                                                        const double* __restrict__ xstats, int xs_ld,
                                                        const __nv_bfloat16* __restrict__ res, int ldr,
                                                        const double* __restrict__ rstats, int rs_ld,
                                                        __nv_bfloat16* __restrict__ out, int ldo, long long S, int C,
-                                                       float eps, int act, float slope) {
+                                                       float eps, int act, float slope, int rev) {
+  extern __shared__ __align__(16) float in_sm[];  // [4][C]: scale, shift of x, then of the residual
   const int tpr = C / 8;
   const int rpb = 256 / tpr;
   const int cv = threadIdx.x % tpr;
   const int rl = threadIdx.x / tpr;
-  if (rl >= rpb) return;
   const int b = blockIdx.y;
   const double inv_n = 1.0 / (double)S;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    in_coeffs(xstats + ((long long)b * xs_ld + c) * 2, inv_n, eps, in_sm[c], in_sm[C + c]);
+    if (RES == 2) in_coeffs(rstats + ((long long)b * rs_ld + c) * 2, inv_n, eps, in_sm[2 * C + c], in_sm[3 * C + c]);
+  }
+  __syncthreads();
   float sc[8], sh[8], rsc[8], rsh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    in_coeffs(xstats + ((long long)b * xs_ld + cv * 8 + j) * 2, inv_n, eps, sc[j], sh[j]);
-    if (RES == 2) in_coeffs(rstats + ((long long)b * rs_ld + cv * 8 + j) * 2, inv_n, eps, rsc[j], rsh[j]);
+    sc[j] = in_sm[cv * 8 + j]; sh[j] = in_sm[C + cv * 8 + j];
+    if (RES == 2) { rsc[j] = in_sm[2 * C + cv * 8 + j]; rsh[j] = in_sm[3 * C + cv * 8 + j]; }
   }
   const __nv_bfloat16* xb = x + (long long)b * S * ldx + cv * 8;
   const __nv_bfloat16* rb = RES ? res + (long long)b * S * ldr + cv * 8 : nullptr;
   __nv_bfloat16* ob = out + (long long)b * S * ldo + cv * 8;
   const long long stride = (long long)gridDim.x * rpb;
-  for (long long r = (long long)blockIdx.x * rpb + rl; r < S; r += stride) {
-    float f[8], g[8];
-    load8(xb + r * ldx, f);
-    if (RES) load8(rb + r * ldr, g);
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  for (long long r0 = (long long)blockIdx.x * rpb + rl; r0 < S; r0 += stride * IN_UNR) {
+    uint4 xq[IN_UNR], rq[IN_UNR];
+    long long rows[IN_UNR];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = fmaf(f[j], sc[j], sh[j]);
-      if (RES == 1) v += g[j];
-      if (RES == 2) v += fmaf(g[j], rsc[j], rsh[j]);
-      if (act) v = v > 0.f ? v : v * slope;
-      f[j] = v;
+    for (int u = 0; u < IN_UNR; ++u) {
+      const long long r = r0 + u * stride;
+      const bool ok = r < S;
+      rows[u] = ok ? (rev ? S - 1 - r : r) : -1;
+      xq[u] = ok ? *reinterpret_cast<const uint4*>(xb + rows[u] * ldx) : z4;
+      if (RES) rq[u] = ok ? *reinterpret_cast<const uint4*>(rb + rows[u] * ldr) : z4;
     }
-    store8(ob + r * ldo, f);
+#pragma unroll
+    for (int u = 0; u < IN_UNR; ++u) {
+      if (rows[u] < 0) continue;
+      float f[8], g[8];
+      unpack8(xq[u], f);
+      if (RES) unpack8(rq[u], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = fmaf(f[j], sc[j], sh[j]);
+        if (RES == 1) v += g[j];
+        if (RES == 2) v += fmaf(g[j], rsc[j], rsh[j]);
+        if (act) v = v > 0.f ? v : v * slope;
+        f[j] = v;
+      }
+      store8(ob + rows[u] * ldo, f);
+    }
   }
 }
 
@@ -343,7 +374,7 @@ extern "C" int ctu_in_apply(const void* x, int ldx, const double* xstats, int xs
   if (!x || !xstats || !out || C % 8 || C > 2048 || (2048 % C) || ldx % 8 || ldo % 8) return CTU_E_BADARG;
   if (res && ldr % 8) return CTU_E_BADARG;
   const int rpb = 256 / (C / 8);
-  int gx = grid_for(S, rpb * 4);
+  int gx = grid_for(S, rpb * 8);
   const int cap = (num_sms() * 8 + B - 1) / B;
   if (gx > cap) gx = cap;
   dim3 grid(gx, B);
@@ -351,12 +382,13 @@ extern "C" int ctu_in_apply(const void* x, int ldx, const double* xstats, int xs
   const __nv_bfloat16* xp = (const __nv_bfloat16*)x;
   const __nv_bfloat16* rp = (const __nv_bfloat16*)res;
   __nv_bfloat16* op = (__nv_bfloat16*)out;
+  const size_t smem = (size_t)(rstats ? 4 : 2) * C * sizeof(float);
   if (!res)
-    in_apply_kernel<0><<<grid, 256, 0, st>>>(xp, ldx, xstats, xs_ld, nullptr, 0, nullptr, 0, op, ldo, S, C, eps, act, slope);
+    in_apply_kernel<0, 4><<<grid, 256, smem, st>>>(xp, ldx, xstats, xs_ld, nullptr, 0, nullptr, 0, op, ldo, S, C, eps, act, slope, 1);
   else if (!rstats)
-    in_apply_kernel<1><<<grid, 256, 0, st>>>(xp, ldx, xstats, xs_ld, rp, ldr, nullptr, 0, op, ldo, S, C, eps, act, slope);
+    in_apply_kernel<1, 2><<<grid, 256, smem, st>>>(xp, ldx, xstats, xs_ld, rp, ldr, nullptr, 0, op, ldo, S, C, eps, act, slope, 1);
   else
-    in_apply_kernel<2><<<grid, 256, 0, st>>>(xp, ldx, xstats, xs_ld, rp, ldr, rstats, rs_ld, op, ldo, S, C, eps, act, slope);
+    in_apply_kernel<2, 2><<<grid, 256, smem, st>>>(xp, ldx, xstats, xs_ld, rp, ldr, rstats, rs_ld, op, ldo, S, C, eps, act, slope, 1);
   count_launch();
   return (int)cudaGetLastError();
 }
