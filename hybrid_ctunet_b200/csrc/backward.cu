@@ -484,15 +484,28 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 #pragma unroll
   for (int j = 0; j < V; ++j) acc[j] = 0.f;
   if (cvec < nvec) {
-    for (long long r = (long long)blockIdx.y * RL + rl; r < M; r += (long long)gridDim.y * RL) {
-      if constexpr (sizeof(T) == 2) {
-        float f[8];
-        ld8(reinterpret_cast<const __nv_bfloat16*>(x) + r * ldx + cvec * 8, f);
+    // four rows per iteration, every load issued before the first add
+    constexpr int UNR = 4;
+    const long long stride = (long long)gridDim.y * RL;
+    for (long long r0 = (long long)blockIdx.y * RL + rl; r0 < M; r0 += stride * UNR) {
+      uint4 q[UNR];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += f[j];
-      } else {
-        const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + r * ldx + cvec * 4);
-        acc[0] += f.x; acc[1] += f.y; acc[2] += f.z; acc[3] += f.w;
+      for (int u = 0; u < UNR; ++u) {
+        const long long r = r0 + u * stride;
+        q[u] = r < M ? *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(x) + (r * ldx + cvec * V) * sizeof(T))
+                     : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if constexpr (sizeof(T) == 2) {
+          float f[8];
+          unpack8(q[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        } else {
+          acc[0] += __uint_as_float(q[u].x); acc[1] += __uint_as_float(q[u].y);
+          acc[2] += __uint_as_float(q[u].z); acc[3] += __uint_as_float(q[u].w);
+        }
       }
     }
   }
@@ -887,11 +900,11 @@ extern "C" int ctu_colsum(const void* x, int x_is_f32, long long ldx, long long 
   const int V = x_is_f32 ? 4 : 8;
   if (!x || !out || M <= 0 || N <= 0 || N % V || ldx % V) return CTU_E_BADARG;
   const long long nvec = N / V;
-  const int cw = nvec <= 8 ? 8 : 32;
+  const int cw = nvec <= 8 ? 8 : (nvec <= 16 ? 16 : 32);
   const long long gx = (nvec + cw - 1) / cw;
   if (gx > 0x7fffffffLL) return CTU_E_BADARG;
   const int rl = 256 / cw;
-  long long gy = (M + rl * 8 - 1) / (rl * 8);
+  long long gy = (M + rl * 16 - 1) / (rl * 16);
   const long long cap = ((long long)bw_num_sms() * 16 + gx - 1) / gx;
   if (gy > cap) gy = cap;
   if (gy > 65535) gy = 65535;
@@ -900,9 +913,11 @@ extern "C" int ctu_colsum(const void* x, int x_is_f32, long long ldx, long long 
   cudaStream_t st = (cudaStream_t)stream;
   if (x_is_f32) {
     if (cw == 8) colsum_kernel<float, 8><<<grid, 256, 0, st>>>((const float*)x, ldx, M, N, out);
+    else if (cw == 16) colsum_kernel<float, 16><<<grid, 256, 0, st>>>((const float*)x, ldx, M, N, out);
     else colsum_kernel<float, 32><<<grid, 256, 0, st>>>((const float*)x, ldx, M, N, out);
   } else {
     if (cw == 8) colsum_kernel<bf16, 8><<<grid, 256, 0, st>>>((const bf16*)x, ldx, M, N, out);
+    else if (cw == 16) colsum_kernel<bf16, 16><<<grid, 256, 0, st>>>((const bf16*)x, ldx, M, N, out);
     else colsum_kernel<bf16, 32><<<grid, 256, 0, st>>>((const bf16*)x, ldx, M, N, out);
   }
   count_launch();

@@ -82,6 +82,19 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erf_v);
 }
 
+// d/dx of the exact-erf GELU: Phi(x) + x phi(x), same erf approximation (one exponential serves both terms)
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float ex = __expf(-z * z);  // exp(-x^2 / 2)
+  const float erf_v = copysignf(1.0f - poly * t * ex, x);
+  return fmaf(x * 0.3989422804014327f, ex, 0.5f * (1.0f + erf_v));
+}
+
 template <int BN, int STAGES, int OUT_BUFS, int CTAS_PER_SM>
 __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB,
@@ -305,6 +318,19 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
               f = unpack_bf16x2(rv.y); v[j + 2] += f.x; v[j + 3] += f.y;
               f = unpack_bf16x2(rv.z); v[j + 4] += f.x; v[j + 5] += f.y;
               f = unpack_bf16x2(rv.w); v[j + 6] += f.x; v[j + 7] += f.y;
+            }
+          }
+        } else if (p.res_mode == CTU_RES_GELU_BWD && valid) {
+          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + out_row * p.ldr + ocol;
+#pragma unroll
+          for (int j = 0; j < CH; j += 8) {
+            if (kFull || gcol + j < p.n_real) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(rp + j);
+              float2 f;
+              f = unpack_bf16x2(rv.x); v[j] *= gelu_erf_grad(f.x); v[j + 1] *= gelu_erf_grad(f.y);
+              f = unpack_bf16x2(rv.y); v[j + 2] *= gelu_erf_grad(f.x); v[j + 3] *= gelu_erf_grad(f.y);
+              f = unpack_bf16x2(rv.z); v[j + 4] *= gelu_erf_grad(f.x); v[j + 5] *= gelu_erf_grad(f.y);
+              f = unpack_bf16x2(rv.w); v[j + 6] *= gelu_erf_grad(f.x); v[j + 7] *= gelu_erf_grad(f.y);
             }
           }
         }

@@ -577,8 +577,10 @@ class Engine:
 
     # ------------------------------------------------------------------ primitives (forward + recorded backward)
     def gemm(self, a, kind: str, name: str, out, *, dims, extra=None, stats=None, act=ACT_NONE, residual=None,
-             out_mode=OUT_BF16, a_c=None, a_needs_grad: bool = True):
-        """Tensor-core contraction through ctu_umma_gemm with the packed weight (kind, name)."""
+             out_mode=OUT_BF16, a_c=None, a_needs_grad: bool = True, a_gelu_of=None):
+        """Tensor-core contraction through ctu_umma_gemm with the packed weight (kind, name).  `a_gelu_of`: `a` is
+        gelu(a_gelu_of) computed without a tape record; the input-gradient GEMM then applies the GELU derivative in
+        its epilogue and hands the gradient to the pre-activation directly."""
         pw = self.w.get(kind, name, extra)
         ac = int(a_c if a_c is not None else pw.a_c)
         ops.gemm(a, pw, out, dims=dims, stats=stats, act=act, residual=residual, out_mode=out_mode, a_c=ac)
@@ -620,7 +622,11 @@ class Engine:
             if a_needs_grad:
                 pt = self.w.get_t(kind, name, extra)
                 cur = self._g(a)
-                if cur is not None and cur.dtype == BF16 and ksize == 1 and cur.shape[-1] == ac:
+                if a_gelu_of is not None:
+                    da = self._empty(*a_gelu_of.shape)
+                    ops.gemm(g16, pt, da, dims=dims, a_c=n_eff, gelu_bwd_of=a_gelu_of)
+                    self._acc(a_gelu_of, da)
+                elif cur is not None and cur.dtype == BF16 and ksize == 1 and cur.shape[-1] == ac:
                     # a gradient has already arrived for `a` (e.g. through the residual connection): let the GEMM
                     # epilogue add it instead of running a separate accumulation pass (in place, row for row)
                     ops.gemm(g16, pt, cur, dims=dims, a_c=n_eff, residual=cur)
@@ -903,13 +909,17 @@ class Engine:
         h = self.layernorm(x, pre + ".net.0", self._empty(M, D))
         n1, n2 = pre + ".net.1", pre + ".net.4"
         hidden = self.w.linear(n1).n_real
+        pre_act = None
         if self.tape is None:
             f = self.gemm(h, "lin", n1, self._empty(M, hidden), dims=(M, 1, 1, 1), extra=True, act=ACT_GELU)
         else:
-            f = self.gelu(self.gemm(h, "lin", n1, self._empty(M, hidden), dims=(M, 1, 1, 1), extra=True))
+            # training keeps the pre-activation; the GELU backward is fused into the epilogue of the down-projection's
+            # input-gradient GEMM (no tape record for the activation itself)
+            pre_act = self.gemm(h, "lin", n1, self._empty(M, hidden), dims=(M, 1, 1, 1), extra=True)
+            f = ops.gelu(pre_act, self._empty(M, hidden))
         out = self._empty(M, D, dtype=out_dtype or x.dtype)
         return self.gemm(f, "lin", n2, out, dims=(M, 1, 1, 1), extra=True, residual=x,
-                         out_mode=OUT_F32 if out.dtype == F32 else OUT_BF16)
+                         out_mode=OUT_F32 if out.dtype == F32 else OUT_BF16, a_gelu_of=pre_act)
 
     def vit_attention(self, pre: str, x, B: int, n: int, heads: int):
         """vit.py:66-78 + residual (vit.py:94); x: fp32 [B*n, D]; returns the updated stream."""

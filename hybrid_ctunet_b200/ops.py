@@ -17,7 +17,7 @@ from .lib import GemmDesc, WgradDesc, check
 
 OUT_BF16, OUT_F32, OUT_F32_CF = 0, 1, 2
 ACT_NONE, ACT_GELU = 0, 1
-RES_NONE, RES_BF16, RES_F32 = 0, 1, 2
+RES_NONE, RES_BF16, RES_F32, RES_GELU_BWD = 0, 1, 2, 3
 
 
 def _stream() -> int:
@@ -82,13 +82,14 @@ def pack_matrix(w2d: torch.Tensor, *, ksize: int = 1, a_c: Optional[int] = None,
 
 def gemm(a: torch.Tensor, w: PackedWeight, out: torch.Tensor, *, dims: Sequence[int], out_mode: int = OUT_BF16,
          act: int = ACT_NONE, residual: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
-         out_col0: int = 0, a_c: Optional[int] = None) -> torch.Tensor:
+         out_col0: int = 0, a_c: Optional[int] = None, gelu_bwd_of: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = epilogue(A (*) W^T) on the tcgen05 kernel.
 
     a    : bf16, channels-last, last dim stride 1; its row stride (a.stride(-2)) is lda.
     dims : (d1, d2, d3, d4) spatial extents of `a` (d1 fastest, d4 batch).  For a flat token GEMM use
            (M, 1, 1, 1); for a per-batch GEMM that feeds InstanceNorm use (S, 1, 1, B).
     out  : bf16/fp32 rows with row stride out.stride(-2) (OUT_BF16 / OUT_F32) or contiguous NCDHW fp32 (OUT_F32_CF).
+    gelu_bwd_of : bf16 pre-activation x shaped like `out`: out = (A (*) W^T) * gelu'(x) (instead of a residual).
     """
     lib = _lib.require_device()
     d1, d2, d3, d4 = (int(v) for v in dims)
@@ -110,7 +111,11 @@ def gemm(a: torch.Tensor, w: PackedWeight, out: torch.Tensor, *, dims: Sequence[
     d.out_mode = out_mode
     d.ldc = 0 if out_mode == OUT_F32_CF else int(out.stride(-2))
     d.act = act
-    if residual is None:
+    if gelu_bwd_of is not None:
+        assert residual is None and gelu_bwd_of.dtype == torch.bfloat16 and gelu_bwd_of.stride(-1) == 1
+        d.residual = gelu_bwd_of.data_ptr()
+        d.res_mode, d.ldr = RES_GELU_BWD, int(gelu_bwd_of.stride(-2))
+    elif residual is None:
         d.res_mode, d.ldr = RES_NONE, 0
     else:
         assert residual.stride(-1) == 1

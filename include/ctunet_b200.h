@@ -36,6 +36,8 @@ extern "C" {
 #define CTU_RES_NONE 0
 #define CTU_RES_BF16 1
 #define CTU_RES_F32 2
+#define CTU_RES_GELU_BWD 3 /* `residual` = bf16 pre-activation x of a GELU: out = acc * gelu'(x)  (backward of
+                              Linear -> GELU -> Linear: the GELU derivative rides on the input-gradient GEMM) */
 
 /* One tcgen05 tensor-core contraction: out = epilogue(A (*) W^T).
  *   k1=k2=k3=1 : plain GEMM over tokens — nn.Linear (vit.py:36,39,59,62,117; hybrid_CTUNet.py:402,457,465,

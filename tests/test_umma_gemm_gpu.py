@@ -65,6 +65,25 @@ def test_linear_bias_gelu_residual_f32_inplace():
     assert _maxrel(out.float(), ref2) < 2 ** -7
 
 
+@pytest.mark.parametrize("M,K,N", [(864, 768, 3072), (4000, 512, 128), (300, 128, 512)])
+def test_linear_gelu_backward_epilogue(M, K, N):
+    """Input gradient of Linear -> GELU -> Linear: out = (dY W) * gelu'(x) in the GEMM epilogue (CTU_RES_GELU_BWD),
+    against torch autograd of the exact-erf GELU (vit.py:37)."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    dy = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5      # plays W^T of the down-projection
+    x = (torch.randn(M, N, device="cuda", generator=g) * 1.5).to(torch.bfloat16)
+    pw = ops.pack_matrix(w)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(dy, pw, out, dims=(M, 1, 1, 1), gelu_bwd_of=x)
+    xr = x.float().requires_grad_()
+    F.gelu(xr).backward(dy.float() @ w.to(torch.bfloat16).float().t())
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out.float(), xr.grad) < 2 ** -8
+    assert _maxrel(out.float(), xr.grad) < 2 ** -6
+
+
 def test_head_channel_first_f32():
     ops = _ops()
     B, X, Y, Z, Cin, Cout = 2, 8, 12, 16, 64, 14
