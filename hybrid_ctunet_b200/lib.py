@@ -56,7 +56,9 @@ def load(build_if_missing: bool = True):
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB_PATH
+    path = os.environ.get("CTU_LIB") or _build.LIB_PATH  # CTU_LIB: another build of the same library (A/B timing)
+    if "CTU_LIB" in os.environ:
+        build_if_missing = False
     if not os.path.exists(path) or (build_if_missing and not _build.is_fresh() and _have_nvcc()):
         if not build_if_missing:
             raise CtuError(f"{path} is missing; run `python -m hybrid_ctunet_b200.build`")
