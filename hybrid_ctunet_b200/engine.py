@@ -360,6 +360,9 @@ class Engine:
         self.side: Optional[torch.cuda.Stream] = None
         self.lane = 0
         self.two_lanes = os.environ.get("CTU_TWO_LANES", "1") != "0"
+        self.wg_stream: Optional[torch.cuda.Stream] = None   # parameter-gradient kernels of the small GEMMs (see _off_path)
+        self._wg_used = False
+        self.off_path_bytes = int(os.environ.get("CTU_OFF_PATH_MB", "16")) << 20
 
     # ------------------------------------------------------------------ helpers
     def _empty(self, *shape, dtype=BF16):
@@ -452,6 +455,25 @@ class Engine:
         if self.tape is not None:
             self.tape.fns.append((self.lane, fn))
 
+    def _off_path(self, fn, tensors):
+        """Run `fn` (parameter-gradient kernels: nothing downstream of them until the gradients are unpacked) off the
+        dependency chain of the backward pass.  While a CUDA graph is being captured and every tensor involved is small
+        (kernels that cannot fill the GPU: the ViT at 864 tokens, the deep encoder stages), they go to a third stream
+        forked from the current one and joined before the gradients are unpacked; otherwise `fn` runs in place."""
+        small = all(t.numel() * t.element_size() <= self.off_path_bytes for t in tensors)
+        if not (self.two_lanes and small and torch.cuda.is_current_stream_capturing()):
+            fn()
+            return
+        if self.wg_stream is None:
+            self.wg_stream = torch.cuda.Stream(device=self.dev)
+        cur = torch.cuda.current_stream()
+        self.wg_stream.wait_stream(cur)
+        for t in tensors:  # not recycled by the capture's allocator before the join
+            t.record_stream(self.wg_stream)
+        with torch.cuda.stream(self.wg_stream):
+            fn()
+        self._wg_used = True
+
     def _side_stream(self) -> torch.cuda.Stream:
         if self.side is None:
             self.side = torch.cuda.Stream(device=self.dev)
@@ -484,6 +506,9 @@ class Engine:
                 fn()
         if used_side:
             main.wait_stream(self.side)
+        if self._wg_used:
+            main.wait_stream(self.wg_stream)
+            self._wg_used = False
         igrads = [None if a is None else self._g(a) for a in want]
         grads = self._finalize_param_grads(tape)
         self.tape = None
@@ -612,11 +637,15 @@ class Engine:
             ksize = pw.ksize
             # parameter gradients
             dw = self.garena.take(ksize ** 3 * ac, n_eff)
-            ops.wgrad(a, g16, dw, dims=dims, ksize=ksize, x_c=ac, n=n_eff)
+            db = self.garena.take(n_eff) if pw.bias is not None else None
+
+            def param_grads():
+                ops.wgrad(a, g16, dw, dims=dims, ksize=ksize, x_c=ac, n=n_eff)
+                if db is not None:
+                    ops.colsum(g16.reshape(-1, g16.shape[-1]) if g16.is_contiguous() else g16, db, n=n_eff)
+            self._off_path(param_grads, (a, g16))
             self.tape.wrecs.append((kind, name, dw, None))
-            if pw.bias is not None:
-                db = self.garena.take(n_eff)
-                ops.colsum(g16.reshape(-1, g16.shape[-1]) if g16.is_contiguous() else g16, db, n=n_eff)
+            if db is not None:
                 self.tape.wrecs.append(("ps_bias" if kind == "ps" else "vec", name if kind == "ps" else name + ".bias", db, None))
             # input gradient
             if a_needs_grad:
