@@ -226,6 +226,65 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TIN* __restrict__ 
   }
 }
 
+// Narrow rows (C = 64 / 128 / 256, bf16 in and out — the per-voxel LayerNorms of the cross-weight fusion and the
+// window-attention blocks at 48·48·96 and 24·24·48): LPR = C/8 lanes own a row (one 16-byte vector each), so a warp
+// covers 32/LPR rows per pass with every lane loading; rows are walked with a grid stride, two rows in flight.
+template <int LPR>
+__global__ void __launch_bounds__(256) layernorm_narrow_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta,
+                                                               __nv_bfloat16* __restrict__ out, long long ldo,
+                                                               long long M, float eps) {
+  constexpr int C = LPR * 8;
+  constexpr int RPB = 256 / LPR;
+  constexpr int UNR = 2;
+  const int sub = threadIdx.x % LPR, rl = threadIdx.x / LPR;
+  float gg[8], bb[8];
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + sub * 8), g1 = *reinterpret_cast<const float4*>(gamma + sub * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + sub * 8), b1 = *reinterpret_cast<const float4*>(beta + sub * 8 + 4);
+    gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w; gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
+    bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+  }
+  const float invC = 1.f / (float)C;
+  const long long stride = (long long)gridDim.x * RPB;
+  // block-uniform trip count: every lane takes part in the shuffles, out-of-range rows are masked
+  const long long iters = (M + stride * UNR - 1) / (stride * UNR);
+  for (long long it = 0; it < iters; ++it) {
+    uint4 q[UNR];
+    long long rows[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long r = ((it * UNR + u) * gridDim.x + blockIdx.x) * RPB + rl;
+      rows[u] = r < M ? r : -1;
+      q[u] = r < M ? *reinterpret_cast<const uint4*>(x + r * ldx + sub * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      float v[8];
+      unpack8(q[u], v);
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[j];
+#pragma unroll
+      for (int o = LPR / 2; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * invC;
+      float sq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; sq += d * d; }
+#pragma unroll
+      for (int o = LPR / 2; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = rsqrtf(sq * invC + eps);
+      if (rows[u] >= 0) {
+        float o8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o8[j] = (v[j] - mean) * rstd * gg[j] + bb[j];
+        store8(out + rows[u] * ldo + sub * 8, o8);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // ViT patch embedding front end (vit.py:115-116): 'b c (h p1) (w p2) (f pf) -> b (h w f) (p1 p2 pf c)', c = 1,
 // fused with LayerNorm(p1*p2*pf).  One block per token, thread = (p1, p2), PF contiguous floats per thread.
@@ -416,6 +475,19 @@ extern "C" int ctu_layernorm(const void* x, int x_is_f32, long long ldx, const f
   if (!x || !gamma || !beta || !out || C % 8 || C > 2048 || ldx % 8 || ldo % 8 || M <= 0) return CTU_E_BADARG;
   if (add && add_rows <= 0) return CTU_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
+  if (!x_is_f32 && !out_is_f32 && !add && (C == 64 || C == 128 || C == 256)) {
+    const int rpb = 256 / (C / 8);
+    const int grid = grid_for(M, rpb * 4);
+#define CTU_LNN(L)                                                                                                  \
+  layernorm_narrow_kernel<L><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, gamma, beta, (__nv_bfloat16*)out, \
+                                                   ldo, M, eps)
+    if (C == 64) CTU_LNN(8);
+    else if (C == 128) CTU_LNN(16);
+    else CTU_LNN(32);
+#undef CTU_LNN
+    count_launch();
+    return (int)cudaGetLastError();
+  }
   if (x_is_f32 && out_is_f32) return launch_ln<float, float>(x, ldx, gamma, beta, add, add_rows, out, ldo, M, C, eps, st);
   if (x_is_f32) return launch_ln<float, __nv_bfloat16>(x, ldx, gamma, beta, add, add_rows, out, ldo, M, C, eps, st);
   if (out_is_f32) return launch_ln<__nv_bfloat16, float>(x, ldx, gamma, beta, add, add_rows, out, ldo, M, C, eps, st);

@@ -643,7 +643,12 @@ class Engine:
                 ops.wgrad(a, g16, dw, dims=dims, ksize=ksize, x_c=ac, n=n_eff)
                 if db is not None:
                     ops.colsum(g16.reshape(-1, g16.shape[-1]) if g16.is_contiguous() else g16, db, n=n_eff)
-            self._off_path(param_grads, (a, g16))
+            # `g` was handed to the residual branch above as ITS gradient buffer, which later contributions are
+            # accumulated into in place: kernels reading it must stay on the dependency chain
+            if residual is not None and g16 is g:
+                param_grads()
+            else:
+                self._off_path(param_grads, (a, g16))
             self.tape.wrecs.append((kind, name, dw, None))
             if db is not None:
                 self.tape.wrecs.append(("ps_bias" if kind == "ps" else "vec", name if kind == "ps" else name + ".bias", db, None))

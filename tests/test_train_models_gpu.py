@@ -123,6 +123,7 @@ def test_graphed_train_step_trains_with_fused_adamw():
     l_eager.backward()
     eager = float(l_eager.detach())
     g_eager = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    del l_eager  # no autograd graph (with AccumulateGrad nodes on the default stream) may survive into the capture
     for p in model.parameters():
         p.grad = None
     step = GraphedTrainStep(model, lambda lg, t: ctunet_loss(lg, t, loss_func), x, y, warmup=1)
@@ -132,12 +133,14 @@ def test_graphed_train_step_trains_with_fused_adamw():
         losses.append(float(step(x, y).detach()))
         if it == 0:
             # the captured step (two lanes + off-path parameter-gradient stream) produces the eager step's gradients
-            # (same kernels; only the order of the fp32 reductions differs)
+            # (same kernels; only the order of the fp32 reductions differs — that noise is re-rounded to bf16 at every
+            # layer of the backward chain and reaches ~3e-3 at the far end, the patch embedding; a race or a lost
+            # contribution would be O(1))
             bad = {}
             for n, p in model.named_parameters():
                 if n in g_eager:
                     e = _rel(p.grad, g_eager[n])
-                    if not e < 2e-3:
+                    if not e < 1e-2:
                         bad[n] = e
                 else:
                     assert p.grad is None, n
