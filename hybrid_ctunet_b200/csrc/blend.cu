@@ -70,14 +70,23 @@ __global__ void __launch_bounds__(256) blend_normalize_kernel(const float* __res
 // (coalesced per channel; the count map is read once instead of C times)
 __global__ void __launch_bounds__(256) blend_normalize_vec_kernel(const float4* __restrict__ acc, const float4* __restrict__ cnt,
                                                                   float4* __restrict__ out, int C, long long vox4) {
+  constexpr int G = 7;  // channels in flight per thread: all G loads are issued before the first division
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < vox4; v += (long long)gridDim.x * blockDim.x) {
     const float4 cn = cnt[v];
-#pragma unroll 2
-    for (int c = 0; c < C; ++c) {
-      const float4 a = acc[(long long)c * vox4 + v];
-      float4 o;
-      o.x = __fdiv_rn(a.x, cn.x); o.y = __fdiv_rn(a.y, cn.y); o.z = __fdiv_rn(a.z, cn.z); o.w = __fdiv_rn(a.w, cn.w);
-      out[(long long)c * vox4 + v] = o;
+    for (int c0 = 0; c0 < C; c0 += G) {
+      float4 a[G];
+#pragma unroll
+      for (int i = 0; i < G; ++i)
+        if (c0 + i < C) a[i] = __ldcs(acc + (long long)(c0 + i) * vox4 + v);
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        if (c0 + i < C) {
+          float4 o;
+          o.x = __fdiv_rn(a[i].x, cn.x); o.y = __fdiv_rn(a[i].y, cn.y); o.z = __fdiv_rn(a[i].z, cn.z);
+          o.w = __fdiv_rn(a[i].w, cn.w);
+          __stcs(out + (long long)(c0 + i) * vox4 + v, o);
+        }
+      }
     }
   }
 }

@@ -2,7 +2,7 @@
 
 Bytes are the tensors each call touches (every distinct tensor argument once: numel x element size), i.e. the
 algorithmic traffic of an HBM-bound kernel; GB/s = bytes / event time.  Output: one line per (op, shapes) class,
-sorted by total time.  `python tools/profile_ops_all.py [B] [json_out]`.
+sorted by total time.  `python tools/profile_ops_all.py [B] [json_out] [--infer]`.
 """
 import collections
 import json
@@ -13,7 +13,7 @@ from hybrid_ctunet_b200 import ops
 from hybrid_ctunet_b200.losses import DiceCELoss, ctunet_loss
 from hybrid_ctunet_b200.networks.hybrid_CTUNet import CTUNet
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 2
 torch.manual_seed(0)
 m = CTUNet(in_channels=1, dim_conv_stem=64, out_channels=14, model_depth=101, img_size=(96, 96), frames=96, patch_frame=8).cuda().train()
 lf = DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6)
@@ -21,7 +21,16 @@ x = torch.rand(B, 1, 96, 96, 96, device="cuda")
 y = torch.randint(0, 14, (B, 1, 96, 96, 96), device="cuda").float()
 
 
+INFER = "--infer" in sys.argv   # forward only, eval mode (one sliding-window call of B windows)
+if INFER:
+    m.eval()
+
+
 def step():
+    if INFER:
+        with torch.no_grad():
+            m(x)
+        return
     for p in m.parameters():
         p.grad = None
     ctunet_loss(m(x), y, lf).backward()
@@ -129,5 +138,5 @@ for ph, d in by_phase.items():
     print(f"\n== phase {ph[0]} {ph[1]}: top classes")
     for k, (n, ms, by) in sorted(d.items(), key=lambda kv: -kv[1][1])[:22]:
         print(f"{ms:8.3f} ms x{n:3d} avg {1e3 * ms / n:7.1f} us {by / ms / 1e6:8.1f} GB/s  {k}")
-if len(sys.argv) > 2:
+if len(sys.argv) > 2 and sys.argv[2].endswith(".json"):
     json.dump({"B": B, "total_ms": tot, "classes": rows}, open(sys.argv[2], "w"), indent=1)
