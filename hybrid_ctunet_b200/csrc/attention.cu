@@ -12,26 +12,35 @@
 
 namespace ctu {
 
-constexpr int KCHUNK = 48;  // keys per online-softmax step (3 k-tiles of 16)
+// One CTA = NW warps x 16 queries of one (window, head); K and V of the whole (window, head) are staged ONCE per CTA
+// as row-major [key][D] tiles (16-byte vector stores only).  The 6^3 windows (n = 216 <= 224) use NW = 14 so that a
+// single CTA owns every query of the (window, head) and nothing is staged twice; the ViT (n = 432, D = 64) uses four
+// warps per CTA and seven CTAs per (batch, head).  The P.V product takes its B fragments from the row-major V tile with
+// ldmatrix.trans (no transposed copy).  KC = keys per online-softmax step.
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
 
-template <int D>
-__global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, int C,
-                                                        __nv_bfloat16* __restrict__ out, int ldo,
-                                                        const float* __restrict__ bias, float scale, int n, int n_pad,
-                                                        TokenMap map, float* __restrict__ lse) {
-  constexpr int LDK = D + 8;
+template <int D, int NW, int KC>
+__global__ void __launch_bounds__(32 * NW) attention_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, int C,
+                                                            __nv_bfloat16* __restrict__ out, int ldo,
+                                                            const float* __restrict__ bias, float scale, int n, int n_pad,
+                                                            TokenMap map, float* __restrict__ lse) {
+  constexpr int LDK = D + 8;   // row pitch 80 / 144 bytes: 16-byte aligned rows, conflict-free fragment and ldmatrix reads
+  constexpr int NT = 32 * NW;
   extern __shared__ __align__(16) uint8_t smem_att[];
   __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_att);  // [n_pad][LDK]
-  const int LDV = n_pad + 8;
-  __nv_bfloat16* Vt = Ks + (size_t)n_pad * LDK;                     // [D][LDV]
+  __nv_bfloat16* Vs = Ks + (size_t)n_pad * LDK;                     // [n_pad][LDK]
 
   const int qt = blockIdx.x, h = blockIdx.y, win = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
 
-  // ---- stage K (row-major) and V (transposed) of this (window, head)
+  // ---- stage K and V of this (window, head)
   constexpr int VPR = D / 8;
-  for (int i = tid; i < n_pad * VPR; i += 128) {
+  for (int i = tid; i < n_pad * VPR; i += NT) {
     const int j = i / VPR, vi = i % VPR;
     uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
     if (j < n) {
@@ -40,13 +49,11 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
       vv = *reinterpret_cast<const uint4*>(rp + 2 * C);
     }
     *reinterpret_cast<uint4*>(Ks + (size_t)j * LDK + vi * 8) = kv;
-    const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) Vt[(size_t)(vi * 8 + e) * LDV + j] = ve[e];
+    *reinterpret_cast<uint4*>(Vs + (size_t)j * LDK + vi * 8) = vv;
   }
 
   // ---- Q fragments (A operand) straight from global memory
-  const int q0 = qt * 64 + warp * 16;
+  const int q0 = qt * (16 * NW) + warp * 16;
   const int qa = q0 + g, qb = q0 + g + 8;
   const bool va = qa < n, vb = qb < n;
   const long long ra = va ? token_row(map, win, qa, n) : 0;
@@ -71,10 +78,10 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
   const float* bias_a = bias ? bias + ((long long)h * n + (va ? qa : 0)) * n : nullptr;
   const float* bias_b = bias ? bias + ((long long)h * n + (vb ? qb : 0)) * n : nullptr;
 
-  for (int k0 = 0; k0 < n_pad; k0 += KCHUNK) {
-    float s[KCHUNK / 8][4];
+  for (int k0 = 0; k0 < n_pad; k0 += KC) {
+    float s[KC / 8][4];
 #pragma unroll
-    for (int j = 0; j < KCHUNK / 8; ++j) {
+    for (int j = 0; j < KC / 8; ++j) {
       s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
       const __nv_bfloat16* kp = Ks + (size_t)(k0 + j * 8 + g) * LDK + 2 * t;
 #pragma unroll
@@ -87,7 +94,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
     // scale (+bias), mask, running max
     float mx_a = -INFINITY, mx_b = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < KCHUNK / 8; ++j) {
+    for (int j = 0; j < KC / 8; ++j) {
       const int key = k0 + j * 8 + 2 * t;
       float ba0 = 0.f, ba1 = 0.f, bb0 = 0.f, bb1 = 0.f;
       if (bias != nullptr && key < n) {
@@ -112,9 +119,9 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
     l_a *= ca; l_b *= cb;
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) { o[i][0] *= ca; o[i][1] *= ca; o[i][2] *= cb; o[i][3] *= cb; }
-    uint32_t pf[KCHUNK / 16][4];
+    uint32_t pf[KC / 16][4];
 #pragma unroll
-    for (int j = 0; j < KCHUNK / 8; ++j) {
+    for (int j = 0; j < KC / 8; ++j) {
       const float p0 = exp2f(s[j][0] - mn_a), p1 = exp2f(s[j][1] - mn_a);
       const float p2 = exp2f(s[j][2] - mn_b), p3 = exp2f(s[j][3] - mn_b);
       l_a += p0 + p1; l_b += p2 + p3;
@@ -123,13 +130,15 @@ __global__ void __launch_bounds__(128) attention_kernel(const __nv_bfloat16* __r
       pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
     }
 #pragma unroll
-    for (int kt = 0; kt < KCHUNK / 16; ++kt) {
+    for (int kt = 0; kt < KC / 16; ++kt) {
+      // lane l addresses row (l & 15) of the 16-key tile, column block (l >> 4) of a pair of 8-wide d blocks
+      const uint32_t vbase = smem_u32(Vs + (size_t)(k0 + kt * 16 + (lane & 15)) * LDK + (lane >> 4) * 8);
 #pragma unroll
-      for (int dn = 0; dn < D / 8; ++dn) {
-        const __nv_bfloat16* vp = Vt + (size_t)(dn * 8 + g) * LDV + k0 + kt * 16 + 2 * t;
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vp);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vp + 8);
-        mma_bf16_16816(o[dn], pf[kt], b0, b1);
+      for (int dn = 0; dn < D / 8; dn += 2) {
+        uint32_t bfr[4];
+        ldmatrix_x4_trans(bfr, vbase + dn * 16);
+        mma_bf16_16816(o[dn], pf[kt], bfr[0], bfr[1]);
+        mma_bf16_16816(o[dn + 1], pf[kt], bfr[2], bfr[3]);
       }
     }
   }
@@ -173,28 +182,37 @@ extern "C" int ctu_attention(const void* qkv, int ld_qkv, int C, int dim_head, v
     windows = batch * m.nwx * m.nwy * m.nwz;
   }
   if (bias && (n % 2)) return CTU_E_BADARG;
-  const int n_pad = (n + KCHUNK - 1) / KCHUNK * KCHUNK;
   const int heads = C / dim_head;
-  const size_t smem = ((size_t)n_pad * (dim_head + 8) + (size_t)dim_head * (n_pad + 8)) * 2;
-  dim3 grid((n + 63) / 64, heads, windows);
   const float scale = 1.0f / sqrtf((float)dim_head);
   cudaStream_t st = (cudaStream_t)stream;
   constexpr int kMaxSmem = 160 * 1024;
-  if (smem > (size_t)kMaxSmem) return CTU_E_UNSUPPORTED;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<64, 4, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    e = cudaFuncSetAttribute(attention_kernel<32, 4, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(attention_kernel<32, 14, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  if (dim_head == 64) {
-    attention_kernel<64><<<grid, 128, smem, st>>>((const __nv_bfloat16*)qkv, ld_qkv, C, (__nv_bfloat16*)out, ldo, bias,
-                                                  scale, n, n_pad, m, lse);
+  const bool one_cta = dim_head == 32 && n <= 224;   // 6^3 windows: one 14-warp CTA per (window, head)
+  const int kc = one_cta ? 32 : 48;
+  const int n_pad = (n + kc - 1) / kc * kc;
+  const size_t smem = (size_t)2 * n_pad * (dim_head + 8) * 2;
+  if (smem > (size_t)kMaxSmem) return CTU_E_UNSUPPORTED;
+  if (one_cta) {
+    dim3 grid(1, heads, windows);
+    attention_kernel<32, 14, 32><<<grid, 32 * 14, smem, st>>>((const __nv_bfloat16*)qkv, ld_qkv, C, (__nv_bfloat16*)out, ldo,
+                                                              bias, scale, n, n_pad, m, lse);
   } else {
-    attention_kernel<32><<<grid, 128, smem, st>>>((const __nv_bfloat16*)qkv, ld_qkv, C, (__nv_bfloat16*)out, ldo, bias,
-                                                  scale, n, n_pad, m, lse);
+    dim3 grid((n + 63) / 64, heads, windows);
+    if (dim_head == 64)
+      attention_kernel<64, 4, 48><<<grid, 128, smem, st>>>((const __nv_bfloat16*)qkv, ld_qkv, C, (__nv_bfloat16*)out, ldo,
+                                                           bias, scale, n, n_pad, m, lse);
+    else
+      attention_kernel<32, 4, 48><<<grid, 128, smem, st>>>((const __nv_bfloat16*)qkv, ld_qkv, C, (__nv_bfloat16*)out, ldo,
+                                                           bias, scale, n, n_pad, m, lse);
   }
   count_launch();
   return (int)cudaGetLastError();
