@@ -11,6 +11,13 @@ bool pdl_enabled() {
   return on;
 }
 
+static std::atomic<int> g_sm_limit{0};
+int persistent_sms(int device_sms) {
+  const int lim = g_sm_limit.load(std::memory_order_relaxed);
+  return (lim > 0 && lim < device_sms) ? lim : device_sms;
+}
+void set_sm_limit(int sms) { g_sm_limit.store(sms, std::memory_order_relaxed); }
+
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 tma_encode_fn tma_encoder() {
@@ -25,6 +32,9 @@ tma_encode_fn tma_encoder() {
 }
 
 }  // namespace ctu
+
+namespace ctu { void set_sm_limit(int); }
+extern "C" void ctu_set_persistent_sm_limit(int sms) { ctu::set_sm_limit(sms); }
 
 extern "C" int64_t ctu_launch_count(void) { return ctu::g_launches.load(std::memory_order_relaxed); }
 

@@ -17,6 +17,8 @@ typedef CUresult (*tma_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 // cuTensorMapEncodeTiled, looked up through the runtime so the library does not link against libcuda.
 tma_encode_fn tma_encoder();
 void count_launch(int n = 1);
+// SMs a persistent tensor-core kernel may occupy (ctu_set_persistent_sm_limit; the device's SM count by default)
+int persistent_sms(int device_sms);
 
 // 3x3x3 convolution with shared-memory halo reuse (umma_conv3_halo.cu); CTU_E_UNSUPPORTED when not applicable.
 int conv3_halo_dispatch(const ::ctu_gemm_desc* d, cudaStream_t stream);

@@ -310,7 +310,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  int cap = halo_sm_count() * CTAS_PER_SM;
+  int cap = persistent_sms(halo_sm_count()) * CTAS_PER_SM;
   if (cap > p.n_tiles) cap -= cap % p.n_tiles;
   const int grid = p.total_tiles < cap ? p.total_tiles : cap;
   const cudaError_t le = launch_pdl(conv3_halo_kernel<BN, SA, SB, CTAS_PER_SM>, dim3(grid), dim3(192), smem, stream, tmA, tmB, tmC, p);

@@ -488,7 +488,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     configured = true;
   }
   // grid: persistent CTAs, a multiple of n_tiles so that every CTA keeps one N tile (per-CTA statistics, L2 reuse)
-  int cap = sm_count() * CTAS_PER_SM;
+  int cap = persistent_sms(sm_count()) * CTAS_PER_SM;
   if (cap > p.n_tiles) cap -= cap % p.n_tiles;
   const int grid = p.total_tiles < cap ? p.total_tiles : cap;
   const cudaError_t le = launch_pdl(umma_gemm_kernel<BN, STAGES, OUT_BUFS, CTAS_PER_SM>, dim3(grid), dim3(192), smem, stream, tmA, tmB, tmC, p);

@@ -272,7 +272,7 @@ static int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmY, WgradPar
     configured = true;
   }
   p.MG = (p.MT + J - 1) / J;
-  const int slots = wg_sm_count() * CTAS_PER_SM;
+  const int slots = persistent_sms(wg_sm_count()) * CTAS_PER_SM;
   const int base = p.MG * p.NT;
   // split the voxel axis so that every CTA slot gets `per_slot` work items: more, shorter items balance the SMs
   // better; fewer, longer items mean fewer fp32 reductions in the epilogue (measured per shape class, see

@@ -258,7 +258,7 @@ static int launch_wh(const CUtensorMap& tmX, const CUtensorMap& tmY, WhParams p,
     configured = true;
   }
   p.SG = (p.MTP + J - 1) / J;
-  const int slots = wh_sm_count() * CTAS_PER_SM;
+  const int slots = persistent_sms(wh_sm_count()) * CTAS_PER_SM;
   const int base = 3 * p.SG * p.NT;
   static const int forced = [] { const char* e = getenv("CTU_WGRAD_ITEMS_PER_SLOT"); return e ? atoi(e) : 0; }();
   if (forced > 0) per_slot = forced;

@@ -363,6 +363,8 @@ class Engine:
         self.wg_stream: Optional[torch.cuda.Stream] = None   # parameter-gradient kernels of the small GEMMs (see _off_path)
         self._wg_used = False
         self.off_path_bytes = int(os.environ.get("CTU_OFF_PATH_MB", "16")) << 20
+        # SMs a persistent tensor-core kernel may take while the two lanes run side by side (0: all of them)
+        self.lane_sms = int(os.environ.get("CTU_LANE_SMS", "0"))
 
     # ------------------------------------------------------------------ helpers
     def _empty(self, *shape, dtype=BF16):
@@ -474,6 +476,10 @@ class Engine:
             fn()
         self._wg_used = True
 
+    def _set_lane_sms(self, on: bool):
+        if self.lane_sms > 0:
+            ops._lib.require_device().ctu_set_persistent_sm_limit(self.lane_sms if on else 0)
+
     def _side_stream(self) -> torch.cuda.Stream:
         if self.side is None:
             # (a higher priority for this, the longer lane, was measured and does not help: 58.4 vs 57.2 ms per step)
@@ -501,6 +507,7 @@ class Engine:
                 for g in tape.grads.values():  # gradients produced on `main` that lane 1 will read (and free)
                     g.record_stream(side)
                 used_side = True
+                self._set_lane_sms(True)
             elif lane == 1 and used_side:
                 with torch.cuda.stream(self.side):
                     fn()
@@ -508,6 +515,7 @@ class Engine:
                 fn()
         if used_side:
             main.wait_stream(self.side)
+            self._set_lane_sms(False)
         if self._wg_used:
             main.wait_stream(self.wg_stream)
             self._wg_used = False
@@ -1091,12 +1099,15 @@ class Engine:
             main, side = torch.cuda.current_stream(), self._side_stream()
             side.wait_stream(main)
             self.lane = 1
+            self._set_lane_sms(True)
             try:
                 with torch.cuda.stream(side):
                     enc, vit_logits, vit_96 = self._vit_branch(x_in, pf, depth, heads)
+                self.lane = 0
+                res = self.resnet("convnet.", x_in, layers)
             finally:
                 self.lane = 0
-            res = self.resnet("convnet.", x_in, layers)
+                self._set_lane_sms(False)
             main.wait_stream(side)
             for t in (*enc, vit_logits, vit_96):
                 t.record_stream(main)

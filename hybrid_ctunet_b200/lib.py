@@ -87,6 +87,8 @@ def _declare(lib):
     lib.ctu_umma_wgrad.restype = C.c_int
     lib.ctu_pack_item_tasks.argtypes = [C.c_int] * 7
     lib.ctu_pack_item_tasks.restype = C.c_longlong
+    lib.ctu_set_persistent_sm_limit.argtypes = [C.c_int]
+    lib.ctu_set_persistent_sm_limit.restype = None
     lib.ctu_launch_count.argtypes = []
     lib.ctu_launch_count.restype = C.c_int64
     lib.ctu_device_ok.argtypes = []

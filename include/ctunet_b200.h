@@ -277,6 +277,11 @@ long long ctu_pack_item_tasks(int unpack, int kind, int rows, int cols, int a, i
 int ctu_pack_weights(const ctu_pack_item* items_dev, int n_items, long long total_units, void* stream);
 int ctu_unpack_grads(const ctu_pack_item* items_dev, int n_items, long long total_units, void* stream);
 
+/* Cap on the SMs a PERSISTENT tensor-core kernel (GEMM / conv / wgrad) sizes its grid for; 0 = all SMs (default).
+ * The engine lowers it while it captures the two concurrent lanes of CTUNet (ViT branch || ResNet encoder,
+ * hybrid_CTUNet.py:821-838) so that one lane's GPU-filling kernel leaves SMs for the other lane's short kernels. */
+void ctu_set_persistent_sm_limit(int sms);
+
 /* Number of kernels this library has launched since load (bench.py's "gpu_launches"). */
 int64_t ctu_launch_count(void);
 /* 1 if the current device is sm_100 and the driver entry points needed for TMA were found. */
