@@ -159,6 +159,15 @@ def _oracle_train_step_seconds(threads: int, warmup: int, steps: int):
     return (time.perf_counter() - t0) / steps
 
 
+_OUT = None
+
+
+def _emit(text: str):
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -168,7 +177,7 @@ def run_reference(args):
     dt = _oracle_train_step_seconds(threads, wu, args.steps)
     value = 1.0 / dt
     sample = f"1 patch (batch 1) per step: oracle CTUNet fp32 fwd + 5-head Dice-CE + autograd bwd on the host cores ({wu} warm-up)"
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": "train_patches_per_s", "value": value, "unit": "patches/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -188,6 +197,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sliding-window", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything a library writes to file descriptor 1 during the run (NCCL's
+    # version banner, for one) is sent to stderr instead
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -355,7 +370,7 @@ def main():
             dt = _oracle_train_step_seconds(threads, 0, 1)
             line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "patches/s", "cores": threads, "kind": "port",
                                     "sample": "1 patch (batch 1), one step, no warm-up: oracle CTUNet fp32 fwd + 5-head Dice-CE + autograd bwd on the host cores"}
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
