@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--optimizer", default="ours", choices=["ours", "torch"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sliding-window", action="store_true")
     args = ap.parse_args()
@@ -231,7 +232,11 @@ def main():
     torch.manual_seed(0)
     model = CTUNet(**KW).to(dev).train()
     loss_func = DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)
+    if args.optimizer == "ours":   # ctu_adamw_step: one multi-tensor launch (hybrid_ctunet_b200/optim.py), same update
+        from hybrid_ctunet_b200.optim import AdamW as CtuAdamW
+        opt = CtuAdamW(model.parameters(), lr=1e-4, weight_decay=1e-5)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)
     reducer = GradientAllReduce(model.parameters(), group) if world > 1 else None
     torch.manual_seed(1 + rank)
     host_x = torch.rand(B, 1, 96, 96, 96).pin_memory()
@@ -351,7 +356,8 @@ def main():
             "config": {"workload": WORKLOAD, "global_batch": patches,
                        "l2": "per-layer activations (0.2-0.9 GB) and the 0.7 GB of weights exceed the 126 MB L2",
                        "parallelism": f"dp{world}: one flat fp32 gradient all-reduce (NCCL) per step" if world > 1 else "single GPU",
-                       "optimizer": "torch.optim.AdamW(fused=True), inside the timed step",
+                       "optimizer": ("hybrid_ctunet_b200.optim.AdamW (ctu_adamw_step, one launch)" if args.optimizer == "ours"
+                                     else "torch.optim.AdamW(fused=True)") + ", inside the timed step",
                        "launch_mode": "forward + loss + backward replayed as one CUDA graph; all-reduce and optimizer eager",
                        "loss": "DiceCE x5 (torch ops on device) + device-side label gather"},
             "tflops_per_gpu": B * FWD_BWD_GFLOP_PER_PATCH / ms,

@@ -1,7 +1,7 @@
 """argtypes/restype declarations for the non-GEMM entry points of include/ctunet_b200.h."""
 import ctypes as C
 
-P, I, L, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+P, I, L, F, D = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
 
 SIGS = {
     "ctu_in_stats": (P, I, I, L, I, P, I, P),
@@ -31,6 +31,7 @@ SIGS = {
     "ctu_cast_f32_bf16": (P, L, P, L, L, I, P),
     "ctu_patchify_ln_bwd": (P, I, I, I, I, I, P, P, P, F, P),
     "ctu_ensemble_argmax": (P, P, I, L, P, P, P, P, P, P),
+    "ctu_adamw_step": (P, I, L, D, D, D, D, D, L, P),
     "ctu_pack_weights": (P, I, L, P),
     "ctu_unpack_grads": (P, I, L, P),
     "ctu_dice_ce_fwd": (P, P, I, I, L, P, P),

@@ -588,7 +588,9 @@ class Engine:
             recs.append((pname, buf, ld, item))
         sig = tuple((pn, buf.data_ptr(), it) for pn, buf, _, it in recs)
         if getattr(self, "_gsig", None) != sig:
-            total = sum(P(pn).numel() for pn, _, _, _ in recs)
+            # every gradient starts on a 16-byte boundary of the flat buffer (vector stores in ctu_unpack_grads,
+            # vector loads in ctu_adamw_step)
+            total = sum(-(-P(pn).numel() // 4) * 4 for pn, _, _, _ in recs)
             self._gflat = torch.empty(total, dtype=F32, device=self.dev)
             self._gtable = ItemTable(self.dev, unpack=True)
             self._gviews = []
@@ -597,7 +599,7 @@ class Engine:
                 n = P(pn).numel()
                 self._gtable.add(buf.data_ptr(), self._gflat.data_ptr() + 4 * off, code, n, ld, a_, b_, c_)
                 self._gviews.append((pn, off, n))
-                off += n
+                off += -(-n // 4) * 4
             self._gsig = sig
         out: Dict[str, torch.Tensor] = {}
         if recs:

@@ -277,6 +277,21 @@ long long ctu_pack_item_tasks(int unpack, int kind, int rows, int cols, int a, i
 int ctu_pack_weights(const ctu_pack_item* items_dev, int n_items, long long total_units, void* stream);
 int ctu_unpack_grads(const ctu_pack_item* items_dev, int n_items, long long total_units, void* stream);
 
+/* Multi-tensor AdamW: the optimizer step of main_CTUNet.py:190-193 (torch.optim.AdamW(lr, weight_decay), no amsgrad) as
+ * ONE launch over a device-resident item table — one item per parameter that has a gradient; all four tensors fp32 and
+ * contiguous, numel elements each; unit0 = index of the item's first work unit (1024 elements per unit), items sorted by
+ * unit0.  `step` is the 1-based step count of these parameters (bias corrections are formed on the host in double). */
+typedef struct ctu_adamw_item {
+  void* param;
+  const void* grad;
+  void* exp_avg;
+  void* exp_avg_sq;
+  int64_t numel;
+  int64_t unit0;
+} ctu_adamw_item;
+int ctu_adamw_step(const ctu_adamw_item* items_dev, int n_items, long long total_units, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, long long step, void* stream);
+
 /* Cap on the SMs a PERSISTENT tensor-core kernel (GEMM / conv / wgrad) sizes its grid for; 0 = all SMs (default).
  * The engine lowers it while it captures the two concurrent lanes of CTUNet (ViT branch || ResNet encoder,
  * hybrid_CTUNet.py:821-838) so that one lane's GPU-filling kernel leaves SMs for the other lane's short kernels. */
