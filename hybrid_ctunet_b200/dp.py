@@ -2,7 +2,8 @@
 
 The reference wraps the model in DistributedDataParallel(find_unused_parameters=True) (main_CTUNet.py:187-189),
 which all-reduces the fp32 gradients in 25 MB buckets while the backward runs.  Here the backward hands back every
-parameter gradient at once (one tape replay), so the exchange is ONE flat fp32 all-reduce (mean) over NVLink per step:
+parameter gradient at once (one tape replay) as slices of ONE flat buffer, so the exchange is ONE fp32 all-reduce (mean)
+of that buffer, in place, over NVLink per step (gradients that live elsewhere are gathered into a flat buffer first):
 about 0.7 GB, ~2 ms at the measured all-reduce bandwidth against ~100 ms of compute.  Parameters whose gradient is
 None (the seven never-used conv3 weights) are skipped and stay None on every rank, as under DDP, so AdamW keeps
 skipping them.  Works over any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests).
@@ -21,20 +22,59 @@ class GradientAllReduce:
         self.group = group
         self._flat: Optional[torch.Tensor] = None
 
+    @staticmethod
+    def _span_view(grads: List[torch.Tensor]) -> Optional[torch.Tensor]:
+        """One flat fp32 view covering every gradient when they are slices of ONE buffer (the engine hands them out as
+        16-byte-aligned slices of its flat unpack buffer), else None.  The view also covers the alignment gaps between
+        slices (at most 3 floats each); whatever they hold is reduced along and never read."""
+        st = grads[0].untyped_storage()
+        base = st.data_ptr()
+        lo, hi, covered = None, 0, 0
+        for g in grads:
+            if g.dtype != torch.float32 or not g.is_contiguous() or g.untyped_storage().data_ptr() != base:
+                return None
+            a = g.storage_offset()
+            lo = a if lo is None else min(lo, a)
+            hi = max(hi, a + g.numel())
+            covered += g.numel()
+        if hi - lo > covered + 4 * len(grads):   # slices of a larger tensor with real data in between: do not touch it
+            return None
+        return torch.empty(0, dtype=torch.float32, device=grads[0].device).set_(st, lo, (hi - lo,))
+
+    def _all_reduce_mean(self, flat: torch.Tensor):
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat.mul_(1.0 / dist.get_world_size(self.group))
+
     def reduce(self) -> int:
         """Average the existing .grad tensors over the group in place; returns the number of elements exchanged."""
         grads = [p.grad for p in self.params if p.grad is not None]
         if not grads:
             return 0
         n = sum(g.numel() for g in grads)
-        if self._flat is None or self._flat.numel() != n or self._flat.device != grads[0].device:
-            self._flat = torch.empty(n, dtype=torch.float32, device=grads[0].device)
+        # gradients that share the most common buffer (the engine's flat unpack buffer) are reduced where they are; the
+        # few that live elsewhere (relative-position tables, repeated parameters) are gathered into a small flat buffer
+        by_storage = {}
+        for g in grads:
+            by_storage.setdefault(g.untyped_storage().data_ptr(), []).append(g)
+        main = max(by_storage.values(), key=lambda gs: sum(g.numel() for g in gs))
+        span = self._span_view(main) if len(main) > 1 else None
+        if span is not None:
+            self._all_reduce_mean(span)
+            ids = {id(g) for g in main}
+            grads = [g for g in grads if id(g) not in ids]
+            if not grads:
+                return n
+        m = sum(g.numel() for g in grads)
+        if self._flat is None or self._flat.numel() != m or self._flat.device != grads[0].device:
+            self._flat = torch.empty(m, dtype=torch.float32, device=grads[0].device)
         views, off = [], 0
         for g in grads:
             views.append(self._flat[off:off + g.numel()].view(g.shape))
             off += g.numel()
         torch._foreach_copy_(views, grads)
-        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group)
-        self._flat.mul_(1.0 / dist.get_world_size(self.group))
+        self._all_reduce_mean(self._flat)
         torch._foreach_copy_(grads, views)
         return n

@@ -51,6 +51,30 @@ def test_gradient_allreduce_is_mean_and_skips_none():
         assert torch.equal(g2, torch.arange(4.0).reshape(2, 2) * 1.5)
 
 
+def _flat_case(rank, world):
+    """Gradients that are aligned slices of ONE flat buffer (how the engine hands them out) are reduced in place."""
+    from hybrid_ctunet_b200.dp import GradientAllReduce
+    params = [torch.nn.Parameter(torch.zeros(3, 5)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
+    flat = torch.full((16 + 8 + 4,), float("nan"))          # gaps between the 16-byte-aligned slices hold garbage
+    views = [flat[0:15].view(3, 5), flat[16:23].view(7), flat[24:28].view(2, 2)]
+    for v, p in zip(views, params):
+        v.fill_(float(rank + 1))
+        p.grad = v
+    ar = GradientAllReduce(params)
+    n = ar.reduce()
+    same_storage = all(p.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr() for p in params)
+    return n, [p.grad.clone() for p in params], same_storage, ar._flat is None
+
+
+def test_gradient_allreduce_in_place_on_one_flat_buffer():
+    out = _run(_flat_case)
+    for rank in (0, 1):
+        n, gs, same, no_copy = out[rank]
+        assert n == 26 and same and no_copy
+        for g in gs:
+            assert torch.equal(g, torch.full_like(g, 1.5))
+
+
 def _shard_case(rank, world):
     """The window ranges the sharded sliding window assigns (hybrid_ctunet_b200/sliding_window.py) tile the window list
     exactly once, contiguously."""
