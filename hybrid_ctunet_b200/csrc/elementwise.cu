@@ -50,10 +50,20 @@ __global__ void __launch_bounds__(256) in_stats_kernel(const __nv_bfloat16* __re
   const int b = blockIdx.y;
   const __nv_bfloat16* xb = x + (long long)b * S * ldx + cv * 8;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (rl < rpb) {
-    for (long long r = (long long)blockIdx.x * rpb + rl; r < S; r += (long long)gridDim.x * rpb) {
+  // four rows in flight per thread, every load issued before the first use
+  constexpr int UNR = 4;
+  const long long stride = (long long)gridDim.x * rpb;
+  for (long long r0 = (long long)blockIdx.x * rpb + rl; r0 < S; r0 += stride * UNR) {
+    uint4 v[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long r = r0 + u * stride;
+      v[u] = r < S ? *reinterpret_cast<const uint4*>(xb + r * ldx) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
       float f[8];
-      load8(xb + r * ldx, f);
+      unpack8(v[u], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
     }
@@ -61,17 +71,13 @@ __global__ void __launch_bounds__(256) in_stats_kernel(const __nv_bfloat16* __re
 #pragma unroll
   for (int j = 0; j < 8; ++j) { red[0][threadIdx.x][j] = s[j]; red[1][threadIdx.x][j] = q[j]; }
   __syncthreads();
-  if (rl == 0) {
-    double ds[8], dq[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { ds[j] = 0; dq[j] = 0; }
-    for (int i = 0; i < rpb; ++i) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { ds[j] += red[0][i * tpr + cv][j]; dq[j] += red[1][i * tpr + cv][j]; }
-    }
-    double* dst = stats + ((long long)b * stats_ld + cv * 8) * 2;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { atomicAdd(dst + 2 * j, ds[j]); atomicAdd(dst + 2 * j + 1, dq[j]); }
+  // one (sum | sum of squares, channel) output per thread over the rpb row slots, then ONE fp64 atomic each
+  for (int o = threadIdx.x; o < 2 * C; o += 256) {
+    const int a = o / C, c = o - a * C;
+    const float* rp = &red[a][c >> 3][c & 7];
+    float acc = 0.f;
+    for (int i = 0; i < rpb; ++i) acc += rp[i * tpr * 8];
+    atomicAdd(stats + ((long long)b * stats_ld + c) * 2 + a, (double)acc);
   }
 }
 
