@@ -360,8 +360,10 @@ class Engine:
         self.side: Optional[torch.cuda.Stream] = None
         self.lane = 0
         self.two_lanes = os.environ.get("CTU_TWO_LANES", "1") != "0"
-        self.wg_stream: Optional[torch.cuda.Stream] = None   # parameter-gradient kernels of the small GEMMs (see _off_path)
+        self.wg_stream: Optional[List[torch.cuda.Stream]] = None   # parameter-gradient kernels of the small GEMMs (_off_path)
         self._wg_used = False
+        self._wg_next = 0
+        self.off_path_streams = max(1, int(os.environ.get("CTU_OFF_PATH_STREAMS", "1")))
         self.off_path_bytes = int(os.environ.get("CTU_OFF_PATH_MB", "16")) << 20
         # SMs a persistent tensor-core kernel may take while the two lanes run side by side (0: all of them)
         self.lane_sms = int(os.environ.get("CTU_LANE_SMS", "0"))
@@ -467,12 +469,14 @@ class Engine:
             fn()
             return
         if self.wg_stream is None:
-            self.wg_stream = torch.cuda.Stream(device=self.dev)
+            self.wg_stream = [torch.cuda.Stream(device=self.dev) for _ in range(self.off_path_streams)]
+        wg = self.wg_stream[self._wg_next % len(self.wg_stream)]
+        self._wg_next += 1
         cur = torch.cuda.current_stream()
-        self.wg_stream.wait_stream(cur)
+        wg.wait_stream(cur)
         for t in tensors:  # not recycled by the capture's allocator before the join
-            t.record_stream(self.wg_stream)
-        with torch.cuda.stream(self.wg_stream):
+            t.record_stream(wg)
+        with torch.cuda.stream(wg):
             fn()
         self._wg_used = True
 
@@ -517,7 +521,8 @@ class Engine:
             main.wait_stream(self.side)
             self._set_lane_sms(False)
         if self._wg_used:
-            main.wait_stream(self.wg_stream)
+            for wg in self.wg_stream:
+                main.wait_stream(wg)
             self._wg_used = False
         igrads = [None if a is None else self._g(a) for a in want]
         grads = self._finalize_param_grads(tape)
