@@ -107,9 +107,11 @@ def test_ctunet_training_step():
     assert float(loss) < l0, (l0, float(loss))
 
 
-def test_graphed_train_step_trains_with_fused_adamw():
-    """CUDA-graph replay of forward + loss + backward (hybrid_ctunet_b200.training): same loss as the eager step on the
-    same weights, and the packed weights follow a FUSED optimizer (which does not bump Tensor._version)."""
+@pytest.mark.parametrize("B,optimizer", [(1, "torch"), (2, "ours")])
+def test_graphed_train_step_trains_with_fused_adamw(B, optimizer):
+    """CUDA-graph replay of forward + loss + backward (hybrid_ctunet_b200.training): same loss and gradients as the eager
+    step on the same weights, and the packed weights follow a FUSED optimizer (which does not bump Tensor._version) —
+    torch's fused AdamW at batch 1, this package's ctu_adamw_step at batch 2 (the bench configuration)."""
     from hybrid_ctunet_b200.losses import DiceCELoss, ctunet_loss
     from hybrid_ctunet_b200.networks.hybrid_CTUNet import CTUNet
     from hybrid_ctunet_b200.training import GraphedTrainStep
@@ -117,8 +119,8 @@ def test_graphed_train_step_trains_with_fused_adamw():
     model = CTUNet(**KW).cuda().train()
     loss_func = DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6)
     torch.manual_seed(1)
-    x = torch.rand(1, 1, 96, 96, 96, device="cuda")
-    y = torch.randint(0, 14, (1, 1, 96, 96, 96), device="cuda").float()
+    x = torch.rand(B, 1, 96, 96, 96, device="cuda")
+    y = torch.randint(0, 14, (B, 1, 96, 96, 96), device="cuda").float()
     l_eager = ctunet_loss(model(x), y, loss_func)
     l_eager.backward()
     eager = float(l_eager.detach())
@@ -127,7 +129,11 @@ def test_graphed_train_step_trains_with_fused_adamw():
     for p in model.parameters():
         p.grad = None
     step = GraphedTrainStep(model, lambda lg, t: ctunet_loss(lg, t, loss_func), x, y, warmup=1)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)
+    if optimizer == "ours":
+        from hybrid_ctunet_b200.optim import AdamW
+        opt = AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5)
+    else:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)
     losses = []
     for it in range(4):
         losses.append(float(step(x, y).detach()))
