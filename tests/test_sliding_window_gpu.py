@@ -59,6 +59,47 @@ def test_full_window_and_overlap_errors():
         sliding_window_inference(x, (32, 32, 32), 4, pred, overlap=1.0)
 
 
+def test_blend_properties_at_the_full_baseline_geometry():
+    """Size-independent properties at BASELINE.json's full geometry (1x1x512x512x256, roi 96^3, overlap 0.5, gaussian,
+    500 windows), where the oracle is too slow to be the checker:
+    partition of unity — a predictor that returns a per-class constant is blended back to that constant;
+    window indexing — a predictor that returns its own input window reconstructs the volume;
+    linearity — blend(2a - 3b) == 2 blend(a) - 3 blend(b) for predictors a, b."""
+    from hybrid_ctunet_b200.trainer_CTUNet import sliding_window_inference
+    shape, roi = (1, 1, 512, 512, 256), (96, 96, 96)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.rand(*shape, device="cuda", generator=g)
+    const = torch.linspace(-3.0, 4.0, 14, device="cuda").view(1, 14, 1, 1, 1)
+    calls = [0]
+
+    def p_const(w):
+        calls[0] += w.shape[0]
+        c = const.expand(w.shape[0], 14, *w.shape[2:])
+        return ((c, c, c), (c * 2, c))
+
+    a0, a1 = sliding_window_inference(x, roi, 4, p_const, overlap=0.5, mode="gaussian")
+    assert calls[0] == 500 and a0.shape == (1, 14, 512, 512, 256)
+    assert (a0 - const).abs().max().item() < 1e-5 and (a1 - 2 * const).abs().max().item() < 1e-5
+    del a0, a1
+
+    def p_ident(w):   # channel c carries (c + 1) * the window itself
+        v = w * torch.arange(1, 15, device="cuda", dtype=w.dtype).view(1, 14, 1, 1, 1)
+        return ((v, v, v), (-v, v))
+
+    b0, b1 = sliding_window_inference(x, roi, 4, p_ident, overlap=0.5, mode="gaussian")
+    for c in (0, 6, 13):
+        assert (b0[0, c] - (c + 1) * x[0, 0]).abs().max().item() < 1e-5 * (c + 1)
+        assert (b1[0, c] + (c + 1) * x[0, 0]).abs().max().item() < 1e-5 * (c + 1)
+
+    def p_lin(w):
+        i, c = p_ident(w), p_const(w)
+        return ((2 * i[0][0] - 3 * c[0][0],) * 3, (2 * i[1][0] - 3 * c[1][0], i[1][1]))
+
+    l0, l1 = sliding_window_inference(x, roi, 4, p_lin, overlap=0.5, mode="gaussian")
+    assert (l0 - (2 * b0 - 3 * const)).abs().max().item() < 2e-4
+    assert (l1 - (2 * b1 - 6 * const)).abs().max().item() < 2e-4
+
+
 def test_ctunet_sliding_window_three_windows():
     """The real predictor: CTUNet(101, pf8) over a 96x96x144 volume (3 windows, overlap 0.5), eager vs CUDA-graph
     replay vs the oracle blend of the same model's logits."""
