@@ -29,6 +29,8 @@ struct HaloParams {
   double* stats;
   int n_real, stats_ld;
   int base_offset_mode;
+  const __nv_bfloat16* residual;  // bf16 rows shaped like the output (may BE the output: in-place accumulation) or NULL
+  int ldr, res_col0;
 };
 
 struct HaloTile {
@@ -217,6 +219,20 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_kernel(const __gr
         uint32_t raw[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN + c0), raw);
         tmem_ld_wait();
+        if (p.residual != nullptr && valid) {
+          // out = acc + residual (the input-gradient convolution adding to a gradient that has already arrived)
+          const long long row = (((long long)t.b * p.d3 + t.x) * p.d2 + (t.y0 + i2)) * p.d1 + (t.z0 + i1);
+          const __nv_bfloat16* rp = p.residual + row * p.ldr + p.res_col0 + t.n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(rp + j);
+            float2 f;
+            f = unpack_bf16x2(rv.x); raw[j] = __float_as_uint(__uint_as_float(raw[j]) + f.x); raw[j + 1] = __float_as_uint(__uint_as_float(raw[j + 1]) + f.y);
+            f = unpack_bf16x2(rv.y); raw[j + 2] = __float_as_uint(__uint_as_float(raw[j + 2]) + f.x); raw[j + 3] = __float_as_uint(__uint_as_float(raw[j + 3]) + f.y);
+            f = unpack_bf16x2(rv.z); raw[j + 4] = __float_as_uint(__uint_as_float(raw[j + 4]) + f.x); raw[j + 5] = __float_as_uint(__uint_as_float(raw[j + 5]) + f.y);
+            f = unpack_bf16x2(rv.w); raw[j + 6] = __float_as_uint(__uint_as_float(raw[j + 6]) + f.x); raw[j + 7] = __float_as_uint(__uint_as_float(raw[j + 7]) + f.y);
+          }
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
@@ -327,8 +343,8 @@ int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
   static const int mode = [] { const char* e = getenv("CTU_CONV_HALO"); return e ? atoi(e) : 1; }();
   if (mode == 0) return CTU_E_UNSUPPORTED;
   if (d->k1 != 3 || d->k2 != 3 || d->k3 != 3) return CTU_E_UNSUPPORTED;
-  if (d->out_mode != CTU_OUT_BF16_ROWS || d->bias || d->residual || d->act != CTU_ACT_NONE || d->convt_cout > 0)
-    return CTU_E_UNSUPPORTED;
+  if (d->out_mode != CTU_OUT_BF16_ROWS || d->bias || d->act != CTU_ACT_NONE || d->convt_cout > 0) return CTU_E_UNSUPPORTED;
+  if (d->residual && (d->res_mode != CTU_RES_BF16 || (d->ldr % 8) != 0)) return CTU_E_UNSUPPORTED;
   if (d->block_n != 64 && d->block_n != 128) return CTU_E_UNSUPPORTED;
   if (d->d1 % 8 != 0 || d->d2 % 16 != 0 || d->a_c % 64 != 0 || d->n_real % 64 != 0) return CTU_E_UNSUPPORTED;
   if (!tma_encoder()) return CTU_E_DRIVER;
@@ -381,6 +397,7 @@ int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
   p.a_c = d->a_c;
   p.stats = d->stats; p.n_real = d->n_real; p.stats_ld = d->stats_ld;
   p.base_offset_mode = 0;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual); p.ldr = d->ldr; p.res_col0 = d->out_col0;
   const long long tiles = (long long)p.T1 * p.T2 * d->d3 * d->d4 * p.n_tiles;
   if (tiles <= 0 || tiles > 0x7fffffffLL) return CTU_E_BADARG;
   p.total_tiles = (int)tiles;

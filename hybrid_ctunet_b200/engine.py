@@ -677,7 +677,7 @@ class Engine:
                     da = self._empty(*a_gelu_of.shape)
                     ops.gemm(g16, pt, da, dims=dims, a_c=n_eff, gelu_bwd_of=a_gelu_of)
                     self._acc(a_gelu_of, da)
-                elif cur is not None and cur.dtype == BF16 and ksize == 1 and cur.shape[-1] == ac:
+                elif cur is not None and cur.dtype == BF16 and pw.convt is None and cur.shape[-1] == ac:
                     # a gradient has already arrived for `a` (e.g. through the residual connection): let the GEMM
                     # epilogue add it instead of running a separate accumulation pass (in place, row for row)
                     ops.gemm(g16, pt, cur, dims=dims, a_c=n_eff, residual=cur)

@@ -124,6 +124,25 @@ def test_conv3x3x3(B, X, Y, Z, Cin, Cout, bn):
     assert torch.allclose(stats[..., 1], (o * o).sum(1), rtol=1e-6, atol=1e-3)
 
 
+@pytest.mark.parametrize("B,X,Y,Z,Cin,Cout,bn", [(1, 8, 16, 32, 64, 64, 64), (2, 6, 32, 16, 128, 128, 128),
+                                                  (1, 12, 16, 24, 64, 128, 64), (1, 5, 7, 9, 64, 64, 64),
+                                                  (1, 6, 6, 12, 256, 256, 128)])
+def test_conv3x3x3_accumulates_in_place(B, X, Y, Z, Cin, Cout, bn):
+    """out = conv(a) + out, in place (the input-gradient convolution adding to a gradient that has already arrived):
+    the halo-reuse kernel where the shape allows it (Y % 16 == 0, Z % 8 == 0), the per-tap kernel otherwise."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(X * Y + Cout)
+    a = torch.randn(B, X, Y, Z, Cin, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(Cout, Cin, 3, 3, 3, device="cuda", generator=g) / (27 * Cin) ** 0.5
+    pw = ops.pack_matrix(_pack_conv3(w), ksize=3, a_c=Cin, block_n=bn)
+    cur = torch.randn(B, X, Y, Z, Cout, device="cuda", generator=g).to(torch.bfloat16)
+    ref = F.conv3d(a.float().permute(0, 4, 1, 2, 3), w.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 4, 1) + cur.float()
+    ops.gemm(a, pw, cur, dims=(Z, Y, X, B), residual=cur)
+    assert torch.isfinite(cur.float()).all()
+    assert _maxrel(cur.float(), ref) < 2 ** -7
+    assert _rel(cur.float(), ref) < 2 ** -8
+
+
 @pytest.mark.parametrize("B,X,Y,Z,Cin,Cout,u", [(1, 6, 6, 12, 128, 64, (2, 2, 2)), (2, 4, 6, 8, 128, 64, (2, 2, 1)),
                                                 (1, 6, 6, 12, 1024, 512, (2, 2, 2))])
 def test_conv_transpose_k_eq_s(B, X, Y, Z, Cin, Cout, u):
