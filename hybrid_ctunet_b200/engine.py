@@ -1092,9 +1092,12 @@ class Engine:
         self._alias(hi, cat, 64)
         self.res_block_cin1("vit_encoder0.layer", x_in, out=hi)
         enc = self.up_attention_block("vit_encoder.", tokens, B, (X // 16, Y // 16, Z // pf), out_last=lo)
+        # the head on `lo` is recorded BEFORE the block that consumes the whole concat buffer: in the backward pass the
+        # block's gradient then becomes the buffer's gradient as it is, and the head's input-gradient GEMM adds into its
+        # `lo` columns in place (the other order zero-fills a 453 MB buffer and runs two accumulation passes)
+        vit_96 = self.head(lo, "lin", "decoder_linear_96x96.head", a_c=64)
         vit_out = self.res_block("vit_decoder0.conv_block", cat, 128, 64)
         vit_logits = self.head(vit_out, "conv1", "vit_out.conv.conv")
-        vit_96 = self.head(lo, "lin", "decoder_linear_96x96.head", a_c=64)
         return enc, vit_logits, vit_96
 
     def ctunet(self, x_in, layers, pf: int, depth: int = 12, heads: int = 12):
