@@ -360,6 +360,8 @@ class Engine:
         self.side: Optional[torch.cuda.Stream] = None
         self.lane = 0
         self.two_lanes = os.environ.get("CTU_TWO_LANES", "1") != "0"
+        self.three_lanes = os.environ.get("CTU_THREE_LANES", "0") != "0"   # vit_encoder0 on a stream of its own
+        self.side2: Optional[torch.cuda.Stream] = None
         self.wg_stream: Optional[List[torch.cuda.Stream]] = None   # parameter-gradient kernels of the small GEMMs (_off_path)
         self._wg_used = False
         self._wg_next = 0
@@ -484,6 +486,11 @@ class Engine:
         if self.lane_sms > 0:
             ops._lib.require_device().ctu_set_persistent_sm_limit(self.lane_sms if on else 0)
 
+    def _side2_stream(self) -> torch.cuda.Stream:
+        if self.side2 is None:
+            self.side2 = torch.cuda.Stream(device=self.dev)
+        return self.side2
+
     def _side_stream(self) -> torch.cuda.Stream:
         if self.side is None:
             # (a higher priority for this, the longer lane, was measured and does not help: 58.4 vs 57.2 ms per step)
@@ -504,19 +511,32 @@ class Engine:
                 tape.grads[_key(t)] = g.contiguous()
         main = torch.cuda.current_stream()
         used_side = False
+        used_side2 = False
         for lane, fn in reversed(tape.fns):
-            if fn is None:  # forward join point: from here back, lane-1 closures run on the side stream, concurrently
+            if fn is None and lane == 0:  # forward join point: from here back, lane-1 closures run on the side stream
                 side = self._side_stream()
                 side.wait_stream(main)
                 for g in tape.grads.values():  # gradients produced on `main` that lane 1 will read (and free)
                     g.record_stream(side)
                 used_side = True
                 self._set_lane_sms(True)
-            elif lane == 1 and used_side:
+            elif fn is None:  # lane 2 joined lane 1 here in the forward: its closures fork off lane 1 from here back
+                if used_side:
+                    side2 = self._side2_stream()
+                    side2.wait_stream(self.side)
+                    for g in tape.grads.values():
+                        g.record_stream(side2)
+                    used_side2 = True
+            elif lane == 2 and used_side2:
+                with torch.cuda.stream(self.side2):
+                    fn()
+            elif lane in (1, 2) and used_side:
                 with torch.cuda.stream(self.side):
                     fn()
             else:
                 fn()
+        if used_side2:
+            main.wait_stream(self.side2)
         if used_side:
             main.wait_stream(self.side)
             self._set_lane_sms(False)
@@ -1083,15 +1103,39 @@ class Engine:
         return feats
 
     # ------------------------------------------------------------------ whole networks
-    def _vit_branch(self, x_in, pf: int, depth: int, heads: int):
+    def _vit_branch(self, x_in, pf: int, depth: int, heads: int, lane2: Optional[torch.cuda.Stream] = None):
+        """ViT -> window-attention decoder -> concat with vit_encoder0 -> vit_decoder0 -> the two ViT-side heads.
+        `lane2`: a third stream for vit_encoder0 (independent of the transformer until the concat): its GPU-filling 96^3
+        kernels then run beside the transformer's long run of small ones, forward and backward."""
         B, _, X, Y, Z = x_in.shape
-        tokens, n = self.vit("vit.", x_in, pf, depth, heads)
         cat = self._empty(B, X, Y, Z, 128)  # torch.cat((vit_enc_96x96, vit_enc0), dim=1) built in place
         lo, hi = cat[..., :64], cat[..., 64:]
         self._alias(lo, cat, 0)
         self._alias(hi, cat, 64)
-        self.res_block_cin1("vit_encoder0.layer", x_in, out=hi)
+        if lane2 is None:
+            tokens, n = self.vit("vit.", x_in, pf, depth, heads)
+            self.res_block_cin1("vit_encoder0.layer", x_in, out=hi)
+        else:
+            # same recording order as the single-stream path (the gradient arena hands out its slices in tape order and
+            # the unpack table built by the eager warm-up step must stay valid), but lane 2 only waits for what precedes
+            # the transformer on this stream
+            fork = torch.cuda.Event()
+            fork.record(torch.cuda.current_stream())   # `cat` was allocated on this lane's stream
+            tokens, n = self.vit("vit.", x_in, pf, depth, heads)
+            lane2.wait_event(fork)
+            cat.record_stream(lane2)
+            prev = self.lane
+            self.lane = 2
+            try:
+                with torch.cuda.stream(lane2):
+                    self.res_block_cin1("vit_encoder0.layer", x_in, out=hi)
+            finally:
+                self.lane = prev
         enc = self.up_attention_block("vit_encoder.", tokens, B, (X // 16, Y // 16, Z // pf), out_last=lo)
+        if lane2 is not None:
+            torch.cuda.current_stream().wait_stream(lane2)
+            if self.tape is not None:
+                self.tape.fns.append((2, None))  # lane 2 joins lane 1 here (forward); the backward forks here
         # the head on `lo` is recorded BEFORE the block that consumes the whole concat buffer: in the backward pass the
         # block's gradient then becomes the buffer's gradient as it is, and the head's input-gradient GEMM adds into its
         # `lo` columns in place (the other order zero-fills a 453 MB buffer and runs two accumulation passes)
@@ -1112,7 +1156,8 @@ class Engine:
             self._set_lane_sms(True)
             try:
                 with torch.cuda.stream(side):
-                    enc, vit_logits, vit_96 = self._vit_branch(x_in, pf, depth, heads)
+                    enc, vit_logits, vit_96 = self._vit_branch(x_in, pf, depth, heads,
+                                                               lane2=self._side2_stream() if self.three_lanes else None)
                 self.lane = 0
                 res = self.resnet("convnet.", x_in, layers)
             finally:
