@@ -17,7 +17,9 @@ def test_header_declares_the_hot_path_entry_points():
     for must in ("ctu_umma_gemm", "ctu_in_apply", "ctu_in_stats", "ctu_layernorm", "ctu_attention", "ctu_pwa_fuse",
                  "ctu_blend_accumulate", "ctu_blend_normalize", "ctu_conv_cin1", "ctu_patchify_ln",
                  "ctu_umma_wgrad", "ctu_in_bwd_stats", "ctu_in_bwd_apply", "ctu_layernorm_bwd", "ctu_attention_bwd",
-                 "ctu_pwa_fuse_bwd", "ctu_gelu_bwd", "ctu_colsum", "ctu_accumulate"):
+                 "ctu_pwa_fuse_bwd", "ctu_gelu_bwd", "ctu_colsum", "ctu_accumulate", "ctu_pack_weights", "ctu_unpack_grads",
+                 "ctu_dice_ce_fwd", "ctu_dice_ce_bwd", "ctu_ensemble_argmax", "ctu_adamw_step",
+                 "ctu_set_persistent_sm_limit"):
         assert must in names
 
 
