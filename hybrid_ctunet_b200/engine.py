@@ -115,8 +115,10 @@ class WeightCache:
 
     def __init__(self, params: Dict[str, torch.Tensor]):
         self.params = params
-        self._cache: Dict[str, list] = {}      # key -> [tag, value, item index or None]
+        self._cache: Dict[str, list] = {}      # key -> [tag, value, item index or None, names, bias repeat(, build)]
         self.items: Optional[ItemTable] = None
+        self.storage_epoch = 0                  # bumped whenever a cached buffer's storage is replaced: CUDA graphs
+                                                # captured over the old buffers are stale from then on
 
     def _tag(self, names):
         ps = [self.params[n.lstrip('.')] for n in names]
@@ -130,7 +132,12 @@ class WeightCache:
             return hit[1]
         with torch.no_grad():
             val = build(*[p.detach() for p in ps])
-        self._cache[key] = [tag, val, None, list(names), 1]
+            if hit is not None and hit[1].shape == val.shape and hit[1].dtype == val.dtype and hit[1].device == val.device \
+                    and hit[1].data_ptr() != val.data_ptr():
+                # keep the buffer a captured CUDA graph may hold the address of: new values, same storage
+                hit[1].copy_(val)
+                val = hit[1]
+        self._cache[key] = [tag, val, None, list(names), 1, build]
         return val
 
     def _packed(self, key: str, wname: str, kind: int, n: int, k: int, *, a: int, b: int, c: int = 0, ksize: int = 1,
@@ -148,6 +155,8 @@ class WeightCache:
         if hit is not None and hit[0][0][0] == tag[0][0] and hit[1].w.device == w.device:
             pw, idx = hit[1], hit[2]          # same storage, new version: re-pack in place
         else:
+            if hit is not None:
+                self.storage_epoch += 1
             bn = block_n or ops.pick_block_n(n)
             n_pad, k_pad = -(-n // bn) * bn, -(-k // 8) * 8
             buf = torch.empty((n_pad, k_pad), dtype=BF16, device=w.device)
@@ -163,7 +172,8 @@ class WeightCache:
         return pw
 
     def refresh_all(self):
-        """Re-pack every registered weight from the parameters' current values with one launch."""
+        """Re-pack every registered weight from the parameters' current values with one launch.  Every packed copy and
+        table keeps its storage (CUDA graphs captured over them stay valid and see the new values)."""
         for ent in self._cache.values():
             if ent[2] is not None and self._tag(ent[3])[1][0][0] != self.items.rows[ent[2]][0]:
                 self.clear()  # a parameter's storage was replaced (e.g. module.to()): start over
@@ -173,8 +183,15 @@ class WeightCache:
         for key in list(self._cache):
             ent = self._cache[key]
             if ent[2] is None:
-                if key.startswith(("d1:", "rb:", "rbT:")):  # small torch-built tables: rebuilt on next use
-                    del self._cache[key]
+                # small torch-built tables (relative-position bias, Cin = 1 conv weights): rebuilt IN PLACE — an inference
+                # CUDA graph captured earlier holds their addresses, so the storage must never be replaced
+                if key.startswith(("d1:", "rb:", "rbT:")):
+                    ps, tag = self._tag(ent[3])
+                    with torch.no_grad():
+                        val = ent[5](*[p.detach() for p in ps])
+                        if val.data_ptr() != ent[1].data_ptr():
+                            ent[1].copy_(val)
+                    ent[0] = tag
                 continue
             if ent[4] != 1:  # pixel-shuffle bias, repeated per sub-voxel
                 ent[1].bias.copy_(self._p(ent[3][1]).detach().to(F32).repeat(ent[4]))
@@ -183,6 +200,7 @@ class WeightCache:
     def clear(self):
         self._cache.clear()
         self.items = None
+        self.storage_epoch += 1
 
     # -- generic access by (kind, name, extra): forward packing and the packing of the dgrad GEMM
     def get(self, kind: str, name: str, extra=None) -> PackedWeight:
@@ -302,7 +320,13 @@ class StatsArena:
     def take(self, B: int, C: int, width: int = 2) -> torch.Tensor:
         n = B * C * width
         if self.off + n > self.buf.numel():
-            raise RuntimeError("InstanceNorm statistics arena exhausted")
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("InstanceNorm statistics arena exhausted during CUDA-graph capture (the eager warm-up "
+                                   "call sizes it: run it with the same batch size)")
+            # grow: slices handed out so far keep the old storage alive (it was zeroed by reset()); from the next
+            # reset() on, everything comes from the larger buffer
+            self.buf = torch.zeros(max(2 * self.buf.numel(), 2 * n), dtype=torch.float64, device=self.buf.device)
+            self.off = 0
         t = self.buf[self.off:self.off + n].view(B, C, width)
         self.off += n
         return t
@@ -612,6 +636,18 @@ class Engine:
                 item = (PACK_VEC, 0, 0, 0)
             recs.append((pname, buf, ld, item))
         sig = tuple((pn, buf.data_ptr(), it) for pn, buf, _, it in recs)
+        gflat = getattr(self, "_gflat", None)
+        if gflat is not None and not torch.cuda.is_current_stream_capturing():
+            # The gradients handed to autograd are views of the persistent flat buffer, and AccumulateGrad keeps such a
+            # view as `.grad` without copying.  If a parameter still holds one (gradient accumulation, zero_grad(
+            # set_to_none=False), a module called twice in one graph), unpacking into the same buffer would overwrite
+            # the accumulated value before autograd adds to it: leave that buffer to the parameters, take a fresh one.
+            base = gflat.untyped_storage().data_ptr()
+            for prm in self.w.params.values():
+                g = getattr(prm, "grad", None)
+                if g is not None and g.untyped_storage().data_ptr() == base:
+                    self._gsig = None
+                    break
         if getattr(self, "_gsig", None) != sig:
             # every gradient starts on a 16-byte boundary of the flat buffer (vector stores in ctu_unpack_grads,
             # vector loads in ctu_adamw_step)
@@ -951,8 +987,11 @@ class Engine:
             return self.in_apply(c3, st3, res=r, rstats=std)
         return self.in_apply(c3, st3, res=x)
 
-    def resnet(self, pre: str, x_in, layers: List[int]):
-        """resnet.py:213-230 (no max pool): stem k7 s(2,2,1) -> IN -> lrelu -> 4 stages; returns 4 feature maps."""
+    def resnet(self, pre: str, x_in, layers: List[int], probe: Optional[Callable] = None):
+        """resnet.py:213-230 (no max pool): stem k7 s(2,2,1) -> IN -> lrelu -> 4 stages; returns 4 feature maps.
+        `probe(name, x) -> x'` (inference only) sees the stem output ("stem") and every block output
+        ("layer{L}.{i}") as channels-last bf16 and may substitute what the NEXT block consumes — the teacher-forced
+        wiring test (SURVEY 8c level 2) drives the real stage loop (strides, down-sample placement, names) this way."""
         B, _, X, Y, Z = x_in.shape
         s0 = DS_STRIDE[0]
         Xo, Yo, Zo = (X + 6 - 7) // s0[0] + 1, (Y + 6 - 7) // s0[1] + 1, (Z + 6 - 7) // s0[2] + 1
@@ -964,11 +1003,16 @@ class Engine:
         x = self.gemm(col, "cin1", pre + "conv1.conv", self._empty(B, Xo, Yo, Zo, 64), dims=(Zo, Yo, Xo, B), stats=st,
                       a_needs_grad=False)
         x = self.in_apply(x, st)
+        if probe is not None:
+            assert self.tape is None
+            x = probe("stem", x)
         feats = []
         strides = [(1, 1, 1), DS_STRIDE[1], DS_STRIDE[2], DS_STRIDE[3]]
         for li, nb in enumerate(layers):
             for bi in range(nb):
                 x = self.bottleneck(f"{pre}layer{li + 1}.{bi}", x, strides[li] if bi == 0 else (1, 1, 1), bi == 0)
+                if probe is not None:
+                    x = probe(f"layer{li + 1}.{bi}", x)
             feats.append(x)
         return feats
 

@@ -55,7 +55,7 @@ class _EngineFn(torch.autograd.Function):
         ctx.module, ctx.eng, ctx.tape, ctx.prog, ctx.n_in = module, eng, eng.tape, prog, n_in
         ctx.stats = eng.stats
         ctx.in_shapes = [t.shape for t in tensors[:n_in]]
-        ctx.names = [n for n, _ in module.named_parameters()]
+        ctx.names = [n for n, _ in module._graph_parameters()]
         eng.tape = None  # a later inference call on the same module must not extend this tape
         outs = tuple(prog.outputs)
         prog.outputs = None
@@ -104,6 +104,18 @@ class KernelModule(nn.Module):
             eng.w.params = params
         return eng
 
+    def _graph_parameters(self):
+        """(name, parameter) pairs that take part in the autograd graph: everything except the weights the forward never
+        reads — `conv3` of a ResBlock with equal in/out channels (hybrid_CTUNet.py:88-91,100-102).  In the reference
+        those are unreachable from the loss, so DistributedDataParallel(find_unused_parameters=True)
+        (main_CTUNet.py:187-189) leaves their .grad None and AdamW never touches them; keeping them out of the graph
+        here gives the same behaviour instead of a zero gradient (which would apply weight decay to them)."""
+        dead = set()
+        for mname, m in self.named_modules():
+            if getattr(m, "downsample", None) is False and hasattr(m, "conv3"):
+                dead.add((mname + "." if mname else "") + "conv3.conv.weight")
+        return [(n, p) for n, p in self.named_parameters() if n not in dead]
+
     def invalidate_weight_cache(self):
         """Drop the packed bf16 copies of the parameters (they are rebuilt on the next call).  The cache notices
         parameter updates through Tensor._version (load_state_dict, copy_, non-fused optimizers); every training forward
@@ -136,7 +148,7 @@ class KernelModule(nn.Module):
         needs = torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
                                              any(x.requires_grad for x in inputs))
         if needs:
-            return _EngineFn.apply(self, len(inputs), *inputs, *self.parameters())
+            return _EngineFn.apply(self, len(inputs), *inputs, *[p for _, p in self._graph_parameters()])
         eng = self._engine()
         eng.tape = None
         with torch.no_grad():

@@ -331,10 +331,22 @@ class _Net(KernelModule):
         if graphs is None:
             graphs = {}
             object.__setattr__(self, "_graphs", graphs)
-        tag = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        # The graph reads the packed bf16 copies / tables of engine.WeightCache.  Those are refreshed IN PLACE (same
+        # storage), so a captured graph stays valid across weight updates: when any parameter's version moved since the
+        # last call they are re-packed with one launch and the graph is replayed.  (Optimizers that update parameters
+        # without bumping Tensor._version are covered by the refresh every training forward and train()/eval() switch
+        # does; hybrid_ctunet_b200.optim.AdamW bumps the versions itself.)  The graph is re-captured only when a
+        # parameter's storage moved (.to(), load_state_dict(assign=True)) or the cache replaced a buffer.
+        params = list(self.parameters())
+        vers = tuple(p._version for p in params)
+        if getattr(self, "_graph_vers", None) != vers:
+            if getattr(self, "_graph_vers", None) is not None:
+                eng.w.refresh_all()
+            object.__setattr__(self, "_graph_vers", vers)
+        tag = (tuple(p.data_ptr() for p in params), eng.w.storage_epoch)
         key = tuple(x.shape)
         ent = graphs.get(key)
-        if ent is not None and ent["tag"] != tag:  # weights changed: packed copies inside the graph are stale
+        if ent is not None and ent["tag"] != tag:
             ent = None
         if ent is None:
             static_x = x.clone()
@@ -344,6 +356,7 @@ class _Net(KernelModule):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 out = self._run(eng, static_x)
+            tag = (tag[0], eng.w.storage_epoch)   # the warm-up call may have (re)built cache entries
             ent = dict(graph=g, x=static_x, out=out, tag=tag)
             graphs[key] = ent
         ent["x"].copy_(x)

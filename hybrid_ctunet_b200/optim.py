@@ -90,4 +90,7 @@ class AdamW(torch.optim.Optimizer):
                 check(lib.ctu_adamw_step(table.data_ptr(), len(ent), units, float(group["lr"]), float(b1), float(b2),
                                          float(group["eps"]), float(group["weight_decay"]), int(s), stream),
                       "ctu_adamw_step")
+                # the kernel writes through raw pointers: tell autograd / the packed-weight caches that the parameters
+                # changed (host-side counter bump, no kernel)
+                torch.autograd.graph.increment_version([e[0] for e in ent])
         return loss

@@ -8,6 +8,10 @@ interval, window starts, importance map) restates MONAI 0.7.0's `dense_patch_sli
 `fall_back_tuple` and `compute_importance_map`; the per-window accumulation and the final divide run in
 ctu_blend_accumulate / ctu_blend_count / ctu_blend_normalize.
 
+`device` (the reference's output/accumulator device, trainer_CTUNet.py:534) selects where the RESULT is returned; the
+fp32 accumulators themselves live on the input's CUDA device, where the blend kernels run (3.76 GB per head at
+512x512x256 against 180 GB of HBM), so `device="cpu"` does not bound GPU memory as it does in the reference.
+
 Differences that do not change results: the count map is kept as ONE channel (the reference accumulates 14
 identical channels, trainer_CTUNet.py:535,543) and is cached per geometry; windows may be sharded over ranks
 (`shard_group`), which only changes the fp32 summation order of overlapping windows.
@@ -156,6 +160,12 @@ def _sliding_window(inputs: torch.Tensor, roi_size, sw_batch_size: int, predicto
         raise NotImplementedError("the CUDA blend path is 3-D (the reference only runs 96^3 windows)")
     if not inputs.is_cuda:
         raise RuntimeError("sliding_window_inference runs on the CUDA blend kernels: inputs must be a CUDA tensor")
+    if sw_device is not None and torch.device(sw_device) != inputs.device and \
+            not (torch.device(sw_device).type == "cuda" and torch.device(sw_device).index is None):
+        # the reference moves each window batch to sw_device (trainer_CTUNet.py:526); here windows are views of
+        # `inputs` consumed in place, so a different window device cannot be honoured — say so instead of ignoring it
+        raise ValueError(f"sw_device={sw_device} differs from inputs.device={inputs.device}: move `inputs` there instead "
+                         "(windows are sliced and blended on the input's CUDA device)")
     image_size_ = list(inputs.shape[2:])
     batch_size = inputs.shape[0]
     out_device = inputs.device if device is None else torch.device(device)
@@ -208,10 +218,16 @@ def _sliding_window(inputs: torch.Tensor, roi_size, sw_batch_size: int, predicto
             b, s = idx // num_win, tuple(int(v) for v in starts[idx % num_win])
             ops.blend_accumulate(p1[j], p2[j] if two_heads else None, imp, acc1[b], acc2[b] if two_heads else None, s)
 
-    if acc1 is None:  # this rank owned no window
-        raise RuntimeError("sliding_window_inference: no window assigned to this rank (more ranks than windows)")
     if shard_group is not None:
         import torch.distributed as dist
+        # a rank that owned no window (fewer windows than ranks) still joins the collectives, with zero accumulators;
+        # it learns the class count from the ranks that ran the predictor
+        ncls = torch.tensor([0 if acc1 is None else acc1.shape[1]], dtype=torch.int64, device=inputs.device)
+        dist.all_reduce(ncls, op=dist.ReduceOp.MAX, group=shard_group)
+        if acc1 is None:
+            acc1 = torch.zeros((batch_size, int(ncls.item())) + image_size, dtype=torch.float32, device=inputs.device)
+            if two_heads:
+                acc2 = torch.zeros_like(acc1)
         dist.all_reduce(acc1, group=shard_group)
         if two_heads:
             dist.all_reduce(acc2, group=shard_group)

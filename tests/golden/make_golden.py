@@ -146,7 +146,63 @@ def whole_nets():
          vit_logits_norm=np.array([v0.double().norm().item(), v0.double().mean().item(), v0.double().std().item()]))
 
 
+def sliding_window_ref():
+    """Outputs of the reference's own two-head sliding_window_inference (trainer_CTUNet.py:417-557, executed through
+    oracle/ref_exec.py) on the shared parity cases: what the CUDA blend must reproduce on the GPU box."""
+    from oracle import ref_exec
+    fn = ref_exec.sliding_window_two_heads()
+    arrs = {}
+    for i, (shape, roi, swb, overlap, mode) in enumerate(ref_exec.SW_CASES):
+        torch.manual_seed(100 + i)
+        vol = torch.rand(shape)
+        h0, h1 = fn(vol, roi, swb, ref_exec.sw_case_predictor(), overlap=overlap, mode=mode)
+        arrs[f"vol{i}"], arrs[f"head0_{i}"], arrs[f"head1_{i}"] = vol, h0, h1
+    save("sliding_window_ref", **arrs)
+
+
+def _bf16_bits(t):
+    return t.to(torch.bfloat16).view(torch.int16).numpy()
+
+
+def resnet_stages():
+    """The reference ResNet-101 encoder (resnet.py:128-245, DS_stride of hybrid_CTUNet.py:728) on one 32^3 patch with
+    TEACHER FORCING at stage granularity: the stem output and every stage output are rounded to bf16 before the next
+    stage consumes them (forward hooks on the unmodified module), so the drop-in, fed the same rounded tensors, is
+    compared stage by stage without inheriting upstream error (SURVEY 8c level 2).  Stored: the rounded stage inputs
+    (bf16 bit patterns) and the reference's fp32 outputs at every 2nd voxel.  Weights: torch.manual_seed(40) default
+    init (the drop-in draws the same values; the probe pins that)."""
+    torch.manual_seed(40)
+    m = resnet.generate_model(101, DS_stride=((2, 2, 1), (2, 2, 2), (2, 2, 2), (2, 2, 2))).eval()
+    torch.manual_seed(41)
+    x = torch.randn(1, 1, 32, 32, 32)
+    raw = {}
+
+    def hook(name):
+        def fn(mod, inp, out):
+            raw[name] = out.clone()
+            return out.to(torch.bfloat16).float()
+        return fn
+    hs = [m.lrelu.register_forward_hook(hook("stem"))]
+    for li in (1, 2, 3, 4):
+        hs.append(getattr(m, f"layer{li}").register_forward_hook(hook(f"layer{li}")))
+    m(x)
+    for h in hs:
+        h.remove()
+    sub = (slice(None), slice(None), slice(None, None, 2), slice(None, None, 2), slice(None, None, 2))
+    arrs = {"x": x}
+    for name in ("stem", "layer1", "layer2", "layer3", "layer4"):
+        arrs["out_" + name] = raw[name][sub]
+        arrs["norm_" + name] = np.array([raw[name].double().norm().item()])
+        if name != "layer4":
+            arrs["teacher_" + name] = _bf16_bits(raw[name])
+    save("resnet101_stages_32", **arrs, **probe_np(m))
+
+
 if __name__ == "__main__":
+    sliding_window_ref()
+    resnet_stages()
+    if "--only-new" in sys.argv:
+        sys.exit(0)
     blocks()
     vit_small()
     up_attention()

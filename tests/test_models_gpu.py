@@ -32,6 +32,15 @@ def _agree(a, b):
     return (a.argmax(1) == b.argmax(1)).double().mean().item()
 
 
+def _margin_agree(a, ref, tol=1e-2):
+    """argmax agreement on the voxels whose fp32 decision is not inside the tolerance band — top-1/top-2
+    margin of the reference logits > 5 x tol x ||logit vector of that voxel||.  Returns (agreement, fraction kept)."""
+    top2 = ref.topk(2, dim=1).values
+    keep = (top2[:, 0] - top2[:, 1]) > 5.0 * tol * ref.norm(dim=1)
+    same = a.argmax(1) == ref.argmax(1)
+    return same[keep].double().mean().item(), keep.double().mean().item()
+
+
 @pytest.fixture(scope="module")
 def ctunet_run():
     from hybrid_ctunet_b200.networks.hybrid_CTUNet import CTUNet
@@ -54,6 +63,8 @@ def ctunet_run():
     for n, a, r, p in zip(names, flat(ours), flat(ref), flat(amp)):
         rows[n] = dict(ours_vs_fp32=_rel(a, r), autocast_vs_fp32=_rel(p.float(), r), ours_argmax=_agree(a, r),
                        autocast_argmax=_agree(p.float(), r), shape=list(a.shape), dtype=str(a.dtype))
+        rows[n]["ours_argmax_margin"], rows[n]["margin_voxels_kept"] = _margin_agree(a, r)
+        rows[n]["autocast_argmax_margin"] = _margin_agree(p.float(), r)[0]
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/parity_ctunet.json", "w") as fh:
         json.dump(rows, fh, indent=1)
@@ -74,6 +85,16 @@ def test_ctunet_vit_heads_meet_bf16_tolerance(ctunet_run):
     for n in ("vit_logits", "vit_96"):
         assert rows[n]["ours_vs_fp32"] <= 1e-2, (n, rows[n])
         assert rows[n]["ours_argmax"] >= rows[n]["autocast_argmax"] - 1e-3, (n, rows[n])
+
+
+def test_ctunet_vit_heads_argmax_999_outside_the_tolerance_band(ctunet_run):
+    """north_star: argmax masks >= 99.9 % voxel-identical, in the measurable form of SURVEY 8c(3): over the voxels
+    whose fp32 top-1/top-2 margin exceeds 5 x (1e-2 x the voxel's logit norm).  (At random init the 14 logits of a voxel
+    are nearly tied for a large share of voxels; inside the band any bf16 implementation, torch's included, flips.)"""
+    rows = ctunet_run["rows"]
+    for n in ("vit_logits", "vit_96"):
+        assert rows[n]["margin_voxels_kept"] > 0.05, (n, rows[n])
+        assert rows[n]["ours_argmax_margin"] >= 0.999, (n, rows[n])
 
 
 def test_ctunet_res_heads_within_autocast_yardstick(ctunet_run):

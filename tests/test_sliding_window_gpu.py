@@ -37,6 +37,29 @@ def test_two_head_blend_bit_exact(shape, roi, overlap, mode):
     assert torch.equal(a0, r0) and torch.equal(a1, r1)
 
 
+def test_cuda_blend_equals_the_reference_functions_output():
+    """tests/golden/sliding_window_ref.npz holds what the reference's OWN sliding_window_inference
+    (trainer_CTUNet.py:417-557, executed unmodified by tests/golden/make_golden.py through oracle/ref_exec.py) returns
+    for the shared parity cases; the CUDA blend over the same logits (the stand-in predictor is evaluated on the CPU,
+    as the fixture's was, so the logits are the same bits) must reproduce it bit for bit."""
+    import os
+    import numpy as np
+    from hybrid_ctunet_b200.trainer_CTUNet import sliding_window_inference
+    from oracle import ref_exec
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sliding_window_ref.npz"))
+    cpu_pred = ref_exec.sw_case_predictor()
+
+    def pred(w):
+        out = cpu_pred(w.cpu())
+        return tuple(tuple(t.cuda() for t in grp) for grp in out)
+
+    for i, (shape, roi, swb, overlap, mode) in enumerate(ref_exec.SW_CASES):
+        vol = torch.from_numpy(z[f"vol{i}"]).cuda()
+        a0, a1 = sliding_window_inference(vol, roi, swb, pred, overlap=overlap, mode=mode)
+        assert torch.equal(a0.cpu(), torch.from_numpy(z[f"head0_{i}"])), i
+        assert torch.equal(a1.cpu(), torch.from_numpy(z[f"head1_{i}"])), i
+
+
 def test_one_head_blend_bit_exact():
     from hybrid_ctunet_b200.trainer_CUNet import sliding_window_inference
     from oracle import sliding_window_oracle as O
