@@ -9,10 +9,14 @@
 //                     across tile boundaries.
 //   warp 1 (1 lane) : MMA issuer — 4 x tcgen05.mma (M128 x BLOCK_N x K16) per K block into one of TWO TMEM
 //                     accumulators; tcgen05.commit frees the smem stage / publishes the accumulator.
-//   warps 2..5      : epilogue — tcgen05.ld (one voxel row per thread), bias / GELU / residual, InstanceNorm
-//                     partial statistics (warp transpose-reduce + fp64 atomics), then either a swizzled smem
-//                     staging tile written back with one TMA store per 64-channel slab (bf16 rows), or direct
-//                     stores (fp32 rows, channel-first heads, transposed-conv scatter).  The epilogue of tile i
+//   warps 2..       : epilogue, 4 or 8 warps (EPI_WARPS; with 8, warps w and w+4 share a TMEM lane quarter and split
+//                     the columns) — tcgen05.ld (one voxel row per thread), bias / GELU / residual, then either a
+//                     swizzled smem staging tile written back with one TMA store per 64-channel slab (bf16 rows),
+//                     or direct stores (fp32 rows, channel-first heads, transposed-conv scatter).  InstanceNorm
+//                     partial statistics of a staged bf16 tile are taken from the STAGED tile by a column-parallel
+//                     pass (each thread walks a pair of columns down a band of rows: 7 instructions per 2 elements,
+//                     no shuffles), accumulated per CTA in registers and flushed with fp64 atomics when the batch
+//                     item changes; the other output modes keep the warp transpose-reduce.  The epilogue of tile i
 //                     overlaps the main loop of tile i+1 through the second accumulator.
 #include "common.cuh"
 #include "../../include/ctunet_b200.h"
@@ -95,8 +99,8 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return fmaf(x * 0.3989422804014327f, ex, 0.5f * (1.0f + erf_v));
 }
 
-template <int BN, int STAGES, int OUT_BUFS, int CTAS_PER_SM>
-__global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, int STAGES, int OUT_BUFS, int CTAS_PER_SM, int EPI_WARPS>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, CTAS_PER_SM) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB,
                                                            const __grid_constant__ CUtensorMap tmC,
                                                            const GemmParams p) {
@@ -106,6 +110,12 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
   constexpr int CH = BN < 32 ? BN : 32;                       // columns per tcgen05.ld
   constexpr int SLABS = BN / 64;                              // 64-channel staging slabs (0: no TMA store path)
   constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, BN);
+  constexpr int EPI_THREADS = 32 * EPI_WARPS;
+  constexpr int COL_SPLIT = EPI_WARPS / 4;                    // warps sharing one TMEM lane quarter
+  constexpr int COLS_PER_WARP = BN / COL_SPLIT;
+  constexpr int SCRATCH = (4 * BN > 2 * EPI_THREADS) ? 4 * BN : 2 * EPI_THREADS;   // float2 entries
+  static_assert(EPI_WARPS == 4 || EPI_WARPS == 8, "epilogue warps");
+  static_assert(COLS_PER_WARP % CH == 0, "column split");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -118,8 +128,8 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
   uint64_t* bar_tfull = bars + 2 * STAGES;
   uint64_t* bar_tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float2* stat_scratch = reinterpret_cast<float2*>(tmem_slot + 2);  // [4][BN]
-  float* bias_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(stat_scratch + 4 * BN) + 15) & ~uintptr_t(15));  // [BN]
+  float2* stat_scratch = reinterpret_cast<float2*>((reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~uintptr_t(15));  // [SCRATCH]
+  float* bias_s = reinterpret_cast<float*>(stat_scratch + SCRATCH);  // [BN]
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5;
@@ -135,7 +145,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_tfull[s]), 1);
-      mbar_init(smem_u32(&bar_tempty[s]), 4);
+      mbar_init(smem_u32(&bar_tempty[s]), EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -201,10 +211,11 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5, 128 threads)
+    // ------------------------------------------------------------------ epilogue (warps 2.., EPI_THREADS threads)
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;
     const int e = threadIdx.x - 64;
+    const int col_lo = ((warp - 2) >> 2) * COLS_PER_WARP;  // this warp's share of the tile's columns
     const int i1 = r % p.b1;
     const int i2 = (r / p.b1) % p.b2;
     const int i3 = r / (p.b1 * p.b2);
@@ -212,21 +223,21 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
     const bool sync_tiles = use_tma || (p.stats != nullptr);
     const long long o1 = (long long)p.d1 * p.u1, o2 = (long long)p.d2 * p.u2, o3 = (long long)p.d3 * p.u3;
 
-    constexpr int STAT_PER_THREAD = (BN + 127) / 128;
+    constexpr int STAT_PER_THREAD = (BN + EPI_THREADS - 1) / EPI_THREADS;
     float acc_s[STAT_PER_THREAD], acc_q[STAT_PER_THREAD];
 #pragma unroll
     for (int k = 0; k < STAT_PER_THREAD; ++k) acc_s[k] = acc_q[k] = 0.f;
     int stat_batch = -1;
     const int n0_cta = (blockIdx.x % p.n_tiles) * BN;
     if (p.bias != nullptr) {  // the grid is a multiple of n_tiles: this CTA only ever sees the N tile n0_cta
-      for (int c = e; c < BN; c += 128) bias_s[c] = (n0_cta + c < p.n_real) ? __ldg(p.bias + n0_cta + c) : 0.f;
-      named_bar_sync(1, 128);
+      for (int c = e; c < BN; c += EPI_THREADS) bias_s[c] = (n0_cta + c < p.n_real) ? __ldg(p.bias + n0_cta + c) : 0.f;
+      named_bar_sync(1, EPI_THREADS);
     }
     auto flush_stats = [&](int b) {
       if (b < 0) return;
 #pragma unroll
       for (int k = 0; k < STAT_PER_THREAD; ++k) {
-        const int c = e + 128 * k;
+        const int c = e + EPI_THREADS * k;
         if (c < BN && n0_cta + c < p.n_real) {
           double* dst = p.stats + ((long long)b * p.stats_ld + n0_cta + c) * 2;
           atomicAdd(dst, (double)acc_s[k]);
@@ -265,8 +276,10 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
           if (OUT_BUFS > 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, EPI_THREADS);
       }
+      // statistics of a staged bf16 tile come from the staged tile itself (column pass below)
+      const bool col_stats = use_tma && (p.stats != nullptr);
 
       // One 32-column chunk of the tile.  kFull (every column of the chunk is a real output column — always, except in
       // the last N tile of the 14-logit heads) folds the per-element range checks away: the HBM-bound GEMMs of this
@@ -339,6 +352,10 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < CH / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          if (col_stats && !valid) {  // rows outside the volume (clipped by the TMA store) must not count
+#pragma unroll
+            for (int j = 0; j < CH / 2; ++j) pk[j] = 0u;
+          }
           if (use_tma) {
             // SWIZZLE_128B staging: row r at r*128, 16-byte chunk c at position (c ^ (r & 7)); the TMA store clips
             // rows / columns outside the output tensor
@@ -361,7 +378,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
                 *reinterpret_cast<uint4*>(op + j) = make_uint4(pk[j / 2], pk[j / 2 + 1], pk[j / 2 + 2], pk[j / 2 + 3]);
             }
           }
-          if (p.stats != nullptr) {
+          if (p.stats != nullptr && !col_stats) {
             // statistics of the values as stored (bf16-rounded), masked rows contribute zero
 #pragma unroll
             for (int j = 0; j < CH / 2; ++j) {
@@ -393,7 +410,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
           }
         }
 
-        if (p.stats != nullptr) {
+        if (p.stats != nullptr && !col_stats) {
           float sq[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
@@ -403,7 +420,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
         }
       };
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += CH) {
+      for (int c0 = col_lo; c0 < col_lo + COLS_PER_WARP; c0 += CH) {
         if (n0 + c0 + CH <= p.n_real) chunk(c0, std::true_type{});
         else chunk(c0, std::false_type{});
       }
@@ -415,7 +432,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
 
       if (sync_tiles) {
         if (use_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        named_bar_sync(2, 128);
+        named_bar_sync(2, EPI_THREADS);
         if (use_tma && e == 0) {
           if constexpr (SLABS > 0) {
 #pragma unroll
@@ -437,14 +454,58 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
             flush_stats(stat_batch);
             stat_batch = tc.t4;
           }
+          if constexpr (SLABS > 0) {
+            if (col_stats) {
+              // Column pass over the staged tile (128 rows x BN bf16, SWIZZLE_128B slabs): thread -> one pair of
+              // adjacent columns (one 32-bit word per row) and a band of RPT rows.  A warp reads 128 contiguous bytes of
+              // one row per step (the swizzle permutes 16-byte chunks inside the row: conflict-free); the eight swizzle
+              // variants of the address are precomputed, so a row costs LDS + 2 unpack + 2 FADD + 2 FFMA.
+              constexpr int PAIRS = BN / 2;
+              constexpr int G = EPI_THREADS / PAIRS;   // row bands
+              constexpr int RPT = BLOCK_M / G;         // rows per thread (multiple of 8)
+              static_assert(EPI_THREADS % PAIRS == 0 && BLOCK_M % G == 0 && RPT % 8 == 0, "column pass tiling");
+              const int pr = e % PAIRS, g = e / PAIRS;
+              const int col = 2 * pr;
+              const uint32_t band = smem_u32(cbuf) + (uint32_t)((col >> 6) * SLAB_BYTES + g * RPT * 128 + (col & 7) * 2);
+              const int chunk16 = (col & 63) >> 3;
+              uint32_t addr8[8];
 #pragma unroll
-          for (int k = 0; k < STAT_PER_THREAD; ++k) {
-            const int c = e + 128 * k;
-            if (c < BN) {
-              const float2 s0 = stat_scratch[c], s1 = stat_scratch[BN + c], s2 = stat_scratch[2 * BN + c],
-                           s3 = stat_scratch[3 * BN + c];
-              acc_s[k] += (s0.x + s1.x) + (s2.x + s3.x);
-              acc_q[k] += (s0.y + s1.y) + (s2.y + s3.y);
+              for (int j = 0; j < 8; ++j) addr8[j] = band + (uint32_t)((chunk16 ^ j) << 4);
+              float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+              for (int i = 0; i < RPT; ++i) {
+                uint32_t w;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(addr8[i & 7] + (uint32_t)(i * 128)) : "memory");
+                const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
+                s0 += lo; s1 += hi;
+                q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
+              }
+              *reinterpret_cast<float4*>(&stat_scratch[g * BN + col]) = make_float4(s0, q0, s1, q1);
+              named_bar_sync(3, EPI_THREADS);
+#pragma unroll
+              for (int k = 0; k < STAT_PER_THREAD; ++k) {
+                const int c = e + EPI_THREADS * k;
+                if (c < BN) {
+#pragma unroll
+                  for (int gg = 0; gg < G; ++gg) {
+                    const float2 sv = stat_scratch[gg * BN + c];
+                    acc_s[k] += sv.x;
+                    acc_q[k] += sv.y;
+                  }
+                }
+              }
+            }
+          }
+          if (!col_stats) {
+#pragma unroll
+            for (int k = 0; k < STAT_PER_THREAD; ++k) {
+              const int c = e + EPI_THREADS * k;
+              if (c < BN) {
+                const float2 s0 = stat_scratch[c], s1 = stat_scratch[BN + c], s2 = stat_scratch[2 * BN + c],
+                             s3 = stat_scratch[3 * BN + c];
+                acc_s[k] += (s0.x + s1.x) + (s2.x + s3.x);
+                acc_q[k] += (s0.y + s1.y) + (s2.y + s3.y);
+              }
             }
           }
         }
@@ -459,10 +520,11 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_gemm_kernel(const __gri
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int STAGES, int OUT_BUFS>
+template <int BN, int STAGES, int OUT_BUFS, int EPI_WARPS>
 constexpr int gemm_smem_bytes() {
+  constexpr int scratch = (4 * BN > 64 * EPI_WARPS) ? 4 * BN : 64 * EPI_WARPS;
   return 1024 + STAGES * (A_STAGE_BYTES + BN * BLOCK_K * 2) + OUT_BUFS * (BN / 64) * SLAB_BYTES + (2 * STAGES + 4) * 8 +
-         16 + 4 * BN * 8 + BN * 4 + 16;
+         32 + scratch * 8 + BN * 4 + 16;
 }
 
 static int sm_count() {
@@ -474,15 +536,15 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES, int OUT_BUFS, int CTAS_PER_SM>
+template <int BN, int STAGES, int OUT_BUFS, int CTAS_PER_SM, int EPI_WARPS = 4>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                        cudaStream_t stream) {
-  constexpr int smem = gemm_smem_bytes<BN, STAGES, OUT_BUFS>();
+  constexpr int smem = gemm_smem_bytes<BN, STAGES, OUT_BUFS, EPI_WARPS>();
   static_assert(CTAS_PER_SM * (smem + 1024) <= 228 * 1024, "shared memory budget");
   static_assert(CTAS_PER_SM * 2 * BN <= 512, "TMEM budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<BN, STAGES, OUT_BUFS, CTAS_PER_SM>,
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<BN, STAGES, OUT_BUFS, CTAS_PER_SM, EPI_WARPS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
@@ -491,7 +553,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   int cap = persistent_sms(sm_count()) * CTAS_PER_SM;
   if (cap > p.n_tiles) cap -= cap % p.n_tiles;
   const int grid = p.total_tiles < cap ? p.total_tiles : cap;
-  const cudaError_t le = launch_pdl(umma_gemm_kernel<BN, STAGES, OUT_BUFS, CTAS_PER_SM>, dim3(grid), dim3(192), smem, stream, tmA, tmB, tmC, p);
+  const cudaError_t le = launch_pdl(umma_gemm_kernel<BN, STAGES, OUT_BUFS, CTAS_PER_SM, EPI_WARPS>, dim3(grid), dim3(64 + 32 * EPI_WARPS), smem, stream, tmA, tmB, tmC, p);
   count_launch();
   return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
@@ -612,14 +674,14 @@ extern "C" int ctu_umma_gemm(const ctu_gemm_desc* d, void* stream_) {
     case 64:
       // 3x3x3 convolutions with 64 output channels: three CTAs per SM (measured 1.04 vs 1.10 ms at 96^3 x 4)
       if (variant == 3 || (variant == 0 && p.num_kb >= 27)) return launch_gemm<64, 2, 1, 3>(tmA, tmB, tmC, p, stream);
-      return launch_gemm<64, 3, 1, 2>(tmA, tmB, tmC, p, stream);
+      return launch_gemm<64, 3, 1, 2, 8>(tmA, tmB, tmC, p, stream);
     case 128:
       // few tiles with a long K loop (ViT GEMMs: 42-168 tiles of 12-48 K blocks): one CTA per SM with a deep ring hides
       // the L2 latency that two 2-stage CTAs cannot when most SMs hold a single tile
       if (variant == 5 || (variant == 0 && p.num_kb >= 8 && p.total_tiles <= 2 * sm_count()))
-        return launch_gemm<128, 5, 1, 1>(tmA, tmB, tmC, p, stream);
-      return launch_gemm<128, 2, 1, 2>(tmA, tmB, tmC, p, stream);
-    case 256: return launch_gemm<256, 3, 1, 1>(tmA, tmB, tmC, p, stream);
+        return launch_gemm<128, 5, 1, 1, 8>(tmA, tmB, tmC, p, stream);
+      return launch_gemm<128, 2, 1, 2, 8>(tmA, tmB, tmC, p, stream);
+    case 256: return launch_gemm<256, 3, 1, 1, 8>(tmA, tmB, tmC, p, stream);
     default: return CTU_E_UNSUPPORTED;
   }
 }

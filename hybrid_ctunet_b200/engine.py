@@ -164,6 +164,8 @@ class WeightCache:
             if bias_name:
                 bias = ps[1].detach().to(F32).contiguous() if bias_repeat == 1 else ps[1].detach().to(F32).repeat(bias_repeat)
             pw = PackedWeight(buf, n, a_c if a_c is not None else k_pad // (ksize ** 3), ksize, bn, convt, bias)
+            # algorithmic work of one GEMM row with the TRUE channel counts (bench.py's per-class roofline)
+            pw.alg_flops_per_row = 2.0 * a * b * (27 if kind in (PACK_CONV3, PACK_CONV3_T) else max(c, 1))
             idx = self.items.add(w.data_ptr(), buf.data_ptr(), kind, n_pad, k_pad, a, b, c)
         if bias_name and bias_repeat != 1:
             pw.bias.copy_(ps[1].detach().to(F32).repeat(bias_repeat))
@@ -713,7 +715,7 @@ class Engine:
             db = self.garena.take(n_eff) if pw.bias is not None else None
 
             def param_grads():
-                ops.wgrad(a, g16, dw, dims=dims, ksize=ksize, x_c=ac, n=n_eff)
+                ops.wgrad(a, g16, dw, dims=dims, ksize=ksize, x_c=ac, n=n_eff, alg_flops_per_row=pw.alg_flops_per_row)
                 if db is not None:
                     ops.colsum(g16.reshape(-1, g16.shape[-1]) if g16.is_contiguous() else g16, db, n=n_eff)
             # `g` was handed to the residual branch above as ITS gradient buffer, which later contributions are
@@ -901,7 +903,7 @@ class Engine:
                 col = self._empty(B, Xo, Yo, Zo, kpad)
                 ops.im2col_cin1(x_in, col, k=k, s=s, p=p)
                 dw = self.garena.take(kpad, 64)
-                ops.wgrad(col, g, dw, dims=(Zo, Yo, Xo, B), x_c=kpad, n=64)
+                ops.wgrad(col, g, dw, dims=(Zo, Yo, Xo, B), x_c=kpad, n=64, alg_flops_per_row=2.0 * taps * 64)
                 self.tape.wrecs.append(("cin1", name, dw, None))
                 self._done(out)
             self._rec(bw)

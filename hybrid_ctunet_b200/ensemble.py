@@ -45,10 +45,12 @@ def hybrid_ctunet_inference(inputs: torch.Tensor, ctunet, tunet, roi_size=(96, 9
     """The "Hybrid-CTUNet" configuration of test_CTUNet_final.py:539-552 for one volume [1, 1, X, Y, Z]: CTUNet's
     ResNet-branch head blended at overlap 0.5, an independently trained TUNet's first head blended at overlap 0.7
     (one-head sliding window), then the mask-complementation ensemble.  Windows are sharded over `shard_group`."""
-    from .sliding_window import sliding_window_inference, sliding_window_inference_one_head
+    from .sliding_window import sliding_window_inference_one_head
     with torch.no_grad():
-        p1 = sliding_window_inference(inputs, roi_size, sw_batch_size, ctunet, overlap=0.5, mode="gaussian",
-                                      shard_group=shard_group)[0]
+        # only CTUNet's ResNet-branch head is used (`[0]` of the two blended heads in the reference script): blend just
+        # that one — half the accumulator traffic and, when sharded, half the bytes on the wire
+        p1 = sliding_window_inference_one_head(inputs, roi_size, sw_batch_size, lambda w: (ctunet(w)[0][0],), overlap=0.5,
+                                               mode="gaussian", shard_group=shard_group)
         p2 = sliding_window_inference_one_head(inputs, roi_size, sw_batch_size, tunet, overlap=0.7, mode="gaussian",
                                                shard_group=shard_group)
         return ensemble_masks(p1[0], p2[0], labels)

@@ -53,6 +53,7 @@ class PackedWeight:
     block_n: int = 64
     convt: Optional[Tuple[int, int, int, int]] = None  # (cout, u1, u2, u3)
     bias: Optional[torch.Tensor] = None                 # fp32 [n_real]
+    alg_flops_per_row: float = 0.0                      # algorithmic FLOPs per GEMM row (true channel counts, no padding)
 
 
 def pick_block_n(n: int) -> int:
@@ -265,13 +266,14 @@ def pick_wgrad_block_n(n: int) -> int:
 
 
 def wgrad(x: torch.Tensor, dy: torch.Tensor, dw: torch.Tensor, *, dims: Sequence[int], ksize: int = 1,
-          x_c: Optional[int] = None, n: Optional[int] = None) -> torch.Tensor:
+          x_c: Optional[int] = None, n: Optional[int] = None, alg_flops_per_row: float = 0.0) -> torch.Tensor:
     """dw[(tap, ci), co] += sum_v x[v + tap - pad, ci] * dy[v, co] on the tcgen05 wgrad kernel.
 
     x  : bf16 channels-last rows (row stride x.stride(-2)), first x_c channels used (x_c % 64 == 0).
     dy : bf16 channels-last rows, first n channels used.
     dw : fp32 [ksize^3 * x_c, >= n] accumulated in place (zero it first).
     dims as for `gemm`: (d1, d2, d3, d4) with d1 fastest; (M, 1, 1, 1) for a flat token GEMM.
+    alg_flops_per_row is bookkeeping for bench.py's per-class roofline (unused here).
     """
     lib = _lib.require_device()
     d1, d2, d3, d4 = (int(v) for v in dims)
