@@ -126,6 +126,7 @@ class KernelClassProbe:
                    "attention": "attention fwd / bwd (mma.sync flash kernels)", "attention_backward": None,
                    "colsum": "glue: column sums, accumulate, casts, layout (space_to_depth, cf_to_cl, subsample, im2col)",
                    "accumulate": None, "cast_f32_bf16": None, "space_to_depth": None, "cf_to_cl": None, "subsample": None,
+                   "head_backward": None,
                    "subsample_backward": None, "im2col_cin1": None, "conv_cin1": None}
 
     def __init__(self, peaks):
@@ -168,7 +169,11 @@ class KernelClassProbe:
                     dims = kwargs["dims"]
                     rows = dims[0] * dims[1] * dims[2] * dims[3]
                     fl = rows * (w.alg_flops_per_row or 2.0 * w.ksize ** 3 * w.a_c * w.n_real)
-                    shape = f"k{w.ksize} {kwargs.get('a_c') or w.a_c}->{w.n_real} rows {rows}"
+                    feat = ("+stats" if kwargs.get("stats") is not None else "") + ("+res" if kwargs.get("residual") is not None else "") + \
+                           ("+gelu" if kwargs.get("act") else "") + ("+gelu_bwd" if kwargs.get("gelu_bwd_of") is not None else "") + \
+                           ("+bias" if w.bias is not None else "") + ("+convt" if w.convt else "") + \
+                           {0: "", 1: " f32", 2: " f32cf"}[kwargs.get("out_mode", 0)]
+                    shape = f"k{w.ksize} {kwargs.get('a_c') or w.a_c}->{w.n_real} rows {rows}{feat}"
                     kind = "conv3" if w.ksize == 3 else ("gemm_t" if fl / max(by, 1) >= probe.ridge else "gemm_h")
                 elif name == "wgrad":
                     dims = kwargs["dims"]
@@ -181,6 +186,8 @@ class KernelClassProbe:
                     kind = "wgrad3" if ks == 3 else ("wgrad_t" if fl / max(by, 1) >= probe.ridge else "wgrad_h")
                 else:
                     kind = name
+                    t0 = next((a for a in args if isinstance(a, torch.Tensor)), None)
+                    shape = f"{name} {tuple(t0.shape) if t0 is not None else ''}"
                 probe.rec.append((kind, shape, e0, e1, fl, by))
                 return r
             return f
@@ -226,7 +233,7 @@ class KernelClassProbe:
             ent = {"class": label, "bound": a["bound"], "achieved": round(ach, 1), "peak": peak, "unit": unit,
                    "frac": round(ach / peak, 4), "ms_per_step": round(a["ms"] / steps, 3),
                    "share_of_step": round(a["ms"] / total, 4), "launches_per_step": a["n"] // steps}
-            if a["shapes"]:
+            if a["shapes"] and label in [v[0] for v in self.CONTRACTIONS.values()]:
                 top = sorted(a["shapes"].items(), key=lambda kv: -kv[1][0])[:3]
                 ent["top_shapes"] = [
                     {"shape": k, "ms_per_step": round(v[0] / steps, 3), "launches_per_step": v[3] // steps,
@@ -234,6 +241,13 @@ class KernelClassProbe:
                     for k, v in top]
             classes.append(ent)
         flops = sum(a["fl"] for a in agg.values())
+        if os.environ.get("CTU_BENCH_DUMP_SHAPES"):   # full per-shape table of every contraction class (profiles/)
+            with open(os.environ["CTU_BENCH_DUMP_SHAPES"], "w") as fh:
+                for label, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+                    fh.write(f"{a['ms'] / steps:8.3f} ms x{a['n'] // steps:4d}  {label}\n")
+                    for k, v in sorted(a["shapes"].items(), key=lambda kv: -kv[1][0]):
+                        fh.write(f"    {v[0] / steps:8.3f} ms x{v[3] // steps:3d} avg {1e3 * v[0] / v[3]:7.1f} us  "
+                                 f"{v[1] / 1e9 / max(v[0], 1e-9):8.1f} TFLOP/s {v[2] / 1e6 / max(v[0], 1e-9):8.1f} GB/s  {k}\n")
         return classes, {"eager_kernel_ms_per_step": round(total / steps, 2), "graph_step_ms": round(graph_step_ms, 2),
                          "whole_step_tflops_vs_peak": round(flops / steps / (graph_step_ms * 1e-3) / 1e12 /
                                                             self.peaks["tf_sustained"], 4),
@@ -511,6 +525,9 @@ def main():
             for it in range(2):
                 if it == 1:
                     probe.install()
+                    # park the GPU on a spin kernel (~0.15 s) while the host enqueues the step: the launches then run
+                    # back to back and an event pair brackets kernel time only, not the host's launch latency
+                    torch.cuda._sleep(int(3e8))
                 for p in model.parameters():
                     p.grad = None
                 ctunet_loss(model(x), y, loss_func).backward()

@@ -24,6 +24,7 @@ SIGS = {
     "ctu_pwa_fuse_bwd": (P, P, P, P, P, L, I, I, P),
     "ctu_colsum": (P, I, L, L, L, P, P),
     "ctu_cf_to_cl": (P, P, I, I, L, I, I, P),
+    "ctu_head_bwd": (P, P, L, P, P, L, I, P, I, P, I, L, I, I, P),
     "ctu_space_to_depth": (P, I, P, I, I, I, I, I, I, I, I, P),
     "ctu_subsample_bwd": (P, I, P, I, I, I, I, I, I, I, I, I, I, P),
     "ctu_im2col_cin1": (P, P, I, I, I, I, I, I, I, I, I, I, I, I, I, I, P),

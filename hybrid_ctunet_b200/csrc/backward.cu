@@ -900,7 +900,7 @@ extern "C" int ctu_colsum(const void* x, int x_is_f32, long long ldx, long long 
   const int V = x_is_f32 ? 4 : 8;
   if (!x || !out || M <= 0 || N <= 0 || N % V || ldx % V) return CTU_E_BADARG;
   const long long nvec = N / V;
-  const int cw = nvec <= 8 ? 8 : (nvec <= 16 ? 16 : 32);
+  const int cw = nvec <= 2 ? 2 : (nvec <= 4 ? 4 : (nvec <= 8 ? 8 : (nvec <= 16 ? 16 : 32)));
   const long long gx = (nvec + cw - 1) / cw;
   if (gx > 0x7fffffffLL) return CTU_E_BADARG;
   const int rl = 256 / cw;
@@ -912,11 +912,15 @@ extern "C" int ctu_colsum(const void* x, int x_is_f32, long long ldx, long long 
   dim3 grid((unsigned)gx, (unsigned)gy);
   cudaStream_t st = (cudaStream_t)stream;
   if (x_is_f32) {
-    if (cw == 8) colsum_kernel<float, 8><<<grid, 256, 0, st>>>((const float*)x, ldx, M, N, out);
+    if (cw == 2) colsum_kernel<float, 2><<<grid, 256, 0, st>>>((const float*)x, ldx, M, N, out);
+    else if (cw == 4) colsum_kernel<float, 4><<<grid, 256, 0, st>>>((const float*)x, ldx, M, N, out);
+    else if (cw == 8) colsum_kernel<float, 8><<<grid, 256, 0, st>>>((const float*)x, ldx, M, N, out);
     else if (cw == 16) colsum_kernel<float, 16><<<grid, 256, 0, st>>>((const float*)x, ldx, M, N, out);
     else colsum_kernel<float, 32><<<grid, 256, 0, st>>>((const float*)x, ldx, M, N, out);
   } else {
-    if (cw == 8) colsum_kernel<bf16, 8><<<grid, 256, 0, st>>>((const bf16*)x, ldx, M, N, out);
+    if (cw == 2) colsum_kernel<bf16, 2><<<grid, 256, 0, st>>>((const bf16*)x, ldx, M, N, out);
+    else if (cw == 4) colsum_kernel<bf16, 4><<<grid, 256, 0, st>>>((const bf16*)x, ldx, M, N, out);
+    else if (cw == 8) colsum_kernel<bf16, 8><<<grid, 256, 0, st>>>((const bf16*)x, ldx, M, N, out);
     else if (cw == 16) colsum_kernel<bf16, 16><<<grid, 256, 0, st>>>((const bf16*)x, ldx, M, N, out);
     else colsum_kernel<bf16, 32><<<grid, 256, 0, st>>>((const bf16*)x, ldx, M, N, out);
   }

@@ -31,6 +31,7 @@ struct HaloParams {
   int base_offset_mode;
   const __nv_bfloat16* residual;  // bf16 rows shaped like the output (may BE the output: in-place accumulation) or NULL
   int ldr, res_col0;
+  int ksteps;  // K16 steps per 64-channel block that can be non-zero (4, or fewer for zero-padded channel rows)
 };
 
 struct HaloTile {
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_kernel(const __gr
                 const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + sb * B_STAGE_BYTES));
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  umma_bf16(acc, da + 2 * k, db + 2 * k, IDESC, (first && k == 0) ? 0u : 1u);
+                  if (k < p.ksteps) umma_bf16(acc, da + 2 * k, db + 2 * k, IDESC, (first && k == 0) ? 0u : 1u);
                 }
                 first = 0;
                 umma_commit(smem_u32(&empty_b[sb]));
@@ -397,6 +398,8 @@ int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
   p.a_c = d->a_c;
   p.stats = d->stats; p.n_real = d->n_real; p.stats_ld = d->stats_ld;
   p.base_offset_mode = 0;
+  // zero-padded channel rows (a_c == 64 with fewer live channels): the K steps over the padding are skipped
+  p.ksteps = (d->a_c == 64 && d->a_c_live > 0 && d->a_c_live < 64) ? (d->a_c_live + 15) / 16 : 4;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual); p.ldr = d->ldr; p.res_col0 = d->out_col0;
   const long long tiles = (long long)p.T1 * p.T2 * d->d3 * d->d4 * p.n_tiles;
   if (tiles <= 0 || tiles > 0x7fffffffLL) return CTU_E_BADARG;

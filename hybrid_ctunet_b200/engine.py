@@ -228,15 +228,18 @@ class WeightCache:
         w = self._p(name + ".weight")
         if kind == "lin":
             n, k = w.shape
-            ncols = 64 if (extra and n < 64) else n   # heads: 14 logits -> the 64-channel padded gradient
+            ncols = -(-n // 16) * 16 if (extra and n < 64) else n   # heads: 14 logits -> the 16-channel padded gradient
             return self._packed("linT:" + name, name + ".weight", PACK_LIN_T, k, ncols, a=n, b=k)
         if kind == "conv1":
             co, ci = w.shape[:2]
-            return self._packed("c1T:" + name, name + ".weight", PACK_LIN_T, _pad64(ci), _pad64(co), a=co, b=ci)
+            kcols = -(-co // 16) * 16 if (extra and co < 64) else _pad64(co)   # biased 1x1x1 conv = logits head
+            return self._packed("c1T:" + name, name + ".weight", PACK_LIN_T, _pad64(ci), kcols, a=co, b=ci)
         if kind == "conv3":
             co, ci = w.shape[:2]
             cop, cip = _pad64(co), _pad64(ci)
-            return self._packed("c3T:" + name, name + ".weight", PACK_CONV3_T, cip, 27 * cop, a=co, b=ci, ksize=3, a_c=cop)
+            pw = self._packed("c3T:" + name, name + ".weight", PACK_CONV3_T, cip, 27 * cop, a=co, b=ci, ksize=3, a_c=cop)
+            pw.a_c_live = -(-co // 16) * 16   # the gradient rows are zero beyond the layer's true output channels
+            return pw
         if kind == "convt":
             ci, co, kx, ky, kz = w.shape
             return self._packed("ctT:" + name, name + ".weight", PACK_CONVT_T, ci, kx * ky * kz * co, a=ci, b=co, c=kx * ky * kz)
@@ -264,7 +267,9 @@ class WeightCache:
     def conv3(self, name: str) -> PackedWeight:
         co, ci = self._p(name + ".weight").shape[:2]
         cop, cip = _pad64(co), _pad64(ci)
-        return self._packed("c3:" + name, name + ".weight", PACK_CONV3, cop, 27 * cip, a=co, b=ci, ksize=3, a_c=cip)
+        pw = self._packed("c3:" + name, name + ".weight", PACK_CONV3, cop, 27 * cip, a=co, b=ci, ksize=3, a_c=cip)
+        pw.a_c_live = -(-ci // 16) * 16       # activation rows are zero beyond the layer's true input channels
+        return pw
 
     # -- ConvTranspose3d kernel == stride [Cin, Cout, kX, kY, kZ]
     def convt(self, name: str) -> PackedWeight:
@@ -694,11 +699,11 @@ class Engine:
                 return
             if residual is not None:
                 self._acc(residual, g)  # identity branch (g stays valid: nothing accumulates into it before we return)
-            if out_mode == OUT_F32_CF:   # logits head: NCDHW fp32 -> channels-last bf16, zero-padded to 64 channels
+            if out_mode == OUT_F32_CF:   # logits head: NCDHW fp32 -> channels-last bf16, zero-padded to 16 channels
                 B, _, X, Y, Z = out.shape
-                g16 = self._empty(B, X, Y, Z, 64)
-                ops.cf_to_cl(g.contiguous(), g16, 64)
-                n_eff = 64
+                n_eff = -(-pw.n_real // 16) * 16   # 32-byte rows: the gradient GEMMs read 14 (+2) channels, not 64
+                g16 = self._empty(B, X, Y, Z, n_eff)
+                ops.cf_to_cl(g.contiguous(), g16, n_eff)
             elif pw.convt is not None:   # up-sampling GEMM: gather the sub-voxels back into GEMM columns
                 co, u1, u2, u3 = pw.convt
                 B, Xo, Yo, Zo, _ = out.shape
@@ -954,7 +959,32 @@ class Engine:
         pw = self.w.get(kind, name, True)
         B, X, Y, Z, _ = x.shape
         out = self._empty(B, pw.n_real, X, Y, Z, dtype=F32)
-        return self.gemm(x, kind, name, out, dims=self._flat_dims(x), extra=True, out_mode=OUT_F32_CF, a_c=a_c)
+        ac = int(a_c if a_c is not None else pw.a_c)
+        if ac not in (64, 128, 256) or pw.n_real > 16:   # shapes outside CTUNet's heads: generic GEMM backward
+            return self.gemm(x, kind, name, out, dims=self._flat_dims(x), extra=True, out_mode=OUT_F32_CF, a_c=a_c)
+        ops.gemm(x, pw, out, dims=self._flat_dims(x), out_mode=OUT_F32_CF, a_c=ac)
+        if self.tape is not None:
+            def bw():
+                # K = N = 14 contractions cannot fill a tensor-core tile: input, weight and bias gradients come from ONE
+                # CUDA-core pass over the fp32 NCDHW logit gradient (ctu_head_bwd) instead of four launches over
+                # 64-channel zero-padded copies of it
+                g = self._g(out)
+                if g is None:
+                    return
+                wparam = self.w._p(name + ".weight").detach()
+                dw, db = self.garena.take(ac, 16), self.garena.take(16)
+                cur = self._g(x)
+                if cur is not None and cur.dtype == BF16 and cur.shape[-1] == ac:
+                    ops.head_backward(g.contiguous(), x, wparam, cur, dw, db, accumulate=True)   # joins in place
+                else:
+                    da = self._empty(*x.shape[:-1], ac)
+                    ops.head_backward(g.contiguous(), x, wparam, da, dw, db)
+                    self._acc(x, da)
+                self.tape.wrecs.append((kind, name, dw, None))
+                self.tape.wrecs.append(("vec", name + ".bias", db, None))
+                self._done(out)
+            self._rec(bw)
+        return out
 
     # ------------------------------------------------------------------ networks/resnet.py
     def bottleneck(self, pre: str, x, stride, has_down: bool):

@@ -54,6 +54,7 @@ class PackedWeight:
     convt: Optional[Tuple[int, int, int, int]] = None  # (cout, u1, u2, u3)
     bias: Optional[torch.Tensor] = None                 # fp32 [n_real]
     alg_flops_per_row: float = 0.0                      # algorithmic FLOPs per GEMM row (true channel counts, no padding)
+    a_c_live: int = 0                                   # 3x3x3 only: input channels that can be non-zero (0 = all a_c)
 
 
 def pick_block_n(n: int) -> int:
@@ -128,6 +129,7 @@ def gemm(a: torch.Tensor, w: PackedWeight, out: torch.Tensor, *, dims: Sequence[
         d.convt_cout, d.u1, d.u2, d.u3 = 0, 1, 1, 1
     d.stats_ld = 0 if stats is None else int(stats.shape[-2])
     d.out_col0 = out_col0
+    d.a_c_live = w.a_c_live if (w.ksize == 3 and 0 < w.a_c_live < ac) else 0
     check(lib.ctu_umma_gemm(C.byref(d), _stream()), "ctu_umma_gemm")
     return out
 
@@ -383,6 +385,23 @@ def cf_to_cl(src: torch.Tensor, dst: torch.Tensor, cpad: int) -> torch.Tensor:
     S = src.numel() // (B * C_)
     check(lib.ctu_cf_to_cl(src.data_ptr(), dst.data_ptr(), B, C_, S, int(dst.stride(-2)), cpad, _stream()), "ctu_cf_to_cl")
     return dst
+
+
+def head_backward(g: torch.Tensor, a: torch.Tensor, w: torch.Tensor, da: torch.Tensor, dw: torch.Tensor,
+                  db: torch.Tensor, accumulate: bool = False) -> None:
+    """Backward of a C -> n_cls logits head in one launch (ctu_head_bwd).  g: fp32 NCDHW [B, ncls, X, Y, Z] contiguous;
+    a / da: bf16 channels-last [B, X, Y, Z, C] (row strides a.stride(-2) / da.stride(-2), da may hold a gradient to add
+    to); w: the fp32 parameter [ncls, C(,1,1,1)]; dw: fp32 [C, ld] accumulated; db: fp32 [>= ncls] accumulated."""
+    lib = _lib.require_device()
+    B, ncls = g.shape[:2]
+    S = g.numel() // (B * ncls)
+    C_ = a.shape[-1]
+    assert g.is_contiguous() and g.dtype == torch.float32 and w.is_contiguous() and w.dtype == torch.float32
+    assert a.dtype == torch.bfloat16 and da.dtype == torch.bfloat16 and a.stride(-1) == 1 and da.stride(-1) == 1
+    assert w.numel() == ncls * C_ and dw.shape[-2] == C_ and dw.stride(-1) == 1
+    check(lib.ctu_head_bwd(g.data_ptr(), a.data_ptr(), int(a.stride(-2)), w.data_ptr(), da.data_ptr(), int(da.stride(-2)),
+                           1 if accumulate else 0, dw.data_ptr(), int(dw.stride(-2)), db.data_ptr(), B, S, C_, ncls,
+                           _stream()), "ctu_head_bwd")
 
 
 def space_to_depth(x: torch.Tensor, out: torch.Tensor, up: Tuple[int, int, int]) -> torch.Tensor:

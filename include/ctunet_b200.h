@@ -68,6 +68,9 @@ typedef struct ctu_gemm_desc {
   int32_t convt_cout, u1, u2, u3;
   int32_t stats_ld;     /* columns per batch in `stats` (>= n_real) */
   int32_t out_col0;     /* first output column inside the ldc-wide output rows (concat-by-offset) */
+  int32_t a_c_live;     /* 0, or a multiple of 16 <= a_c: channels [a_c_live, a_c) of every `a` row are known to be zero
+                           (ResNet layer-1 planes = 32 live in 64-channel rows, resnet.py:181-186): the 3x3x3 kernel skips
+                           their K steps */
 } ctu_gemm_desc;
 
 int ctu_umma_gemm(const ctu_gemm_desc* desc, void* stream);
@@ -183,6 +186,15 @@ int ctu_pwa_fuse_bwd(const void* qkv1, const void* qkv2, const void* dout, void*
 /* out[c] += sum over the M rows of x[row][c], x bf16 or fp32 [M][ldx], N columns (bias gradients, position-embedding
  * gradient, relative-position-bias gradient over windows). */
 int ctu_colsum(const void* x, int x_is_f32, long long ldx, long long M, long long N, float* out, void* stream);
+
+/* Backward of a logits head — UnetOutBlock (1x1x1 conv + bias, hybrid_CTUNet.py:781-783,810) / DecoderLinear
+ * (hybrid_CTUNet.py:671-691) — in one pass: replaces torch's conv/linear backward (input gradient, weight gradient,
+ * bias gradient) for the C -> n_cls heads.  g: NCDHW fp32 logit gradient [B][ncls][S]; a: the head's bf16
+ * channels-last input [B*S][lda] (C channels, C in {64, 128, 256}); w: the fp32 parameter [ncls][C];
+ * da [B*S][ldda] bf16 = g W (added to its previous contents when accumulate != 0); dw fp32 [C][ldw] += a^T g;
+ * db fp32 [ncls] += column sums of g.  ncls <= 16. */
+int ctu_head_bwd(const float* g, const void* a, long long lda, const float* w, void* da, long long ldda,
+                 int accumulate, float* dw, int ldw, float* db, int B, long long S, int C, int ncls, void* stream);
 
 /* NCDHW fp32 [B][C][S] -> channels-last bf16 [B][S][ldd] with channels [C, cpad) zero (logit gradients). */
 int ctu_cf_to_cl(const float* src, void* dst, int B, int C, long long S, int ldd, int cpad, void* stream);

@@ -356,3 +356,40 @@ def test_fused_dice_ce_matches_oracle(shape):
     (ref * 3.0).backward()
     assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
     assert rel(logits.grad, ref_in.grad) < 1e-4
+
+
+@pytest.mark.parametrize("C,shape,ld_extra,acc", [(64, (2, 8, 12, 16), 0, False), (64, (1, 5, 7, 9), 64, True),
+                                                  (128, (1, 6, 6, 12), 0, True), (256, (2, 3, 4, 5), 0, False)])
+def test_head_backward_fused(C, shape, ld_extra, acc):
+    """ctu_head_bwd (input, weight and bias gradient of a C -> 14 logits head in one pass) vs torch autograd of
+    F.conv3d(k=1) + bias on the same bf16-rounded activations; `ld_extra`: the activation / gradient live in a wider
+    concat buffer; `acc`: the input gradient is added to one that has already arrived."""
+    import torch.nn.functional as F
+    from hybrid_ctunet_b200 import ops
+    torch.manual_seed(3)
+    B, X, Y, Z = shape
+    ncls = 14
+    a_full = torch.randn(B, X, Y, Z, C + ld_extra, device="cuda").to(torch.bfloat16)
+    a = a_full[..., :C]
+    w = torch.randn(ncls, C, device="cuda") * 0.1
+    g = torch.randn(B, ncls, X, Y, Z, device="cuda")
+    prev = torch.randn(B, X, Y, Z, C + ld_extra, device="cuda").to(torch.bfloat16)
+    da_full = prev.clone() if acc else torch.full_like(prev, float("nan"))
+    da = da_full[..., :C]
+    dw = torch.zeros(C, 16, device="cuda")
+    db = torch.zeros(16, device="cuda")
+    ops.head_backward(g, a, w, da, dw, db, accumulate=acc)
+    # reference
+    ar = a.float().permute(0, 4, 1, 2, 3).contiguous().requires_grad_()
+    wr = w.clone().requires_grad_()
+    br = torch.zeros(ncls, device="cuda", requires_grad=True)
+    torch.backends.cudnn.allow_tf32 = False
+    F.conv3d(ar, wr.view(ncls, C, 1, 1, 1), br).backward(g)
+    want_da = ar.grad.permute(0, 2, 3, 4, 1)
+    if acc:
+        want_da = want_da + prev[..., :C].float()
+    assert rel(da.float(), want_da) < 5e-3          # bf16 rounding of the stored gradient
+    assert rel(dw[:, :ncls].t(), wr.grad) < 1e-5 and float(dw[:, ncls:].abs().max()) == 0.0
+    assert rel(db[:ncls], br.grad) < 1e-5
+    if ld_extra:   # columns outside the head's slice are untouched
+        assert torch.equal(da_full[..., C:], prev[..., C:]) if acc else torch.isnan(da_full[..., C:].float()).all()
