@@ -480,6 +480,8 @@ def main():
             return CtuAdamW(model.parameters(), lr=1e-4, weight_decay=1e-5)
         return torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)
 
+    dp_chunks = int(os.environ.get("CTU_DP_CHUNKS", "4"))   # 1: one all-reduce, then the optimizer (A/B comparisons)
+
     def timed_training(B: int, probe_classes: bool):
         """Graph capture + warm-up + K timed device-resident steps + K timed end-to-end steps at batch B per GPU."""
         opt = make_optimizer()
@@ -498,7 +500,7 @@ def main():
         def train_step(xd, yd):
             loss = graphed(xd, yd)
             if reducer is not None:
-                reducer.reduce_and_step(opt) if hasattr(reducer, "reduce_and_step") else (reducer.reduce(), opt.step())
+                reducer.reduce_and_step(opt, chunks=dp_chunks)
             else:
                 opt.step()
             return loss

@@ -11,6 +11,10 @@
 // 27 x 16 KB per tile); the weights (one 64 x BN box per tap) stream through their own ring.
 // Epilogue: bf16 rows through a swizzled staging tile + TMA store, InstanceNorm statistics (fp64 atomics), as in
 // umma_gemm.cu.  Used for the 64/128-channel layers whose (z, y) extents are multiples of (8, 16).
+//
+// ZT = 2 (BN = 64, z extent a multiple of 16, opt-in): one CTA computes TWO z-adjacent 128-voxel tiles from one 18 x 18
+// halo box and ONE stream of weight boxes — every weight box feeds two accumulators (L2 -> shared-memory traffic per
+// 128 voxels 285 KB -> 170 KB).  Measured neutral: see conv3_halo_dispatch.
 #include "common.cuh"
 #include "../../include/ctunet_b200.h"
 #include "host_util.h"
@@ -18,10 +22,11 @@
 
 namespace ctu {
 
-constexpr int HALO_Z = 10, HALO_Y = 18;
-constexpr int HALO_A_BYTES = HALO_Z * HALO_Y * 128;  // 23040 bytes written by TMA
-constexpr int HALO_A_STAGE = 23 * 1024;              // ring pitch (1024-byte aligned)
+constexpr int HALO_Y = 18;
 constexpr int HALO_SLAB_BYTES = 128 * 128;
+__host__ __device__ constexpr int halo_z(int zt) { return 8 * zt + 2; }
+__host__ __device__ constexpr int halo_a_bytes(int zt) { return halo_z(zt) * HALO_Y * 128; }                 // written by TMA
+__host__ __device__ constexpr int halo_a_stage(int zt) { return (halo_a_bytes(zt) + 1023) / 1024 * 1024; }  // ring pitch
 
 struct HaloParams {
   int T1, T2, d1, d2, d3, d4;
@@ -38,11 +43,11 @@ struct HaloTile {
   int z0, y0, x, b, n0;
 };
 
-__device__ __forceinline__ HaloTile halo_decode(const HaloParams& p, int tile, int bn) {
+__device__ __forceinline__ HaloTile halo_decode(const HaloParams& p, int tile, int bn, int zext) {
   HaloTile t;
   const int n_tile = tile % p.n_tiles;
   int m = tile / p.n_tiles;
-  t.z0 = (m % p.T1) * 8; m /= p.T1;
+  t.z0 = (m % p.T1) * zext; m /= p.T1;
   t.y0 = (m % p.T2) * 16; m /= p.T2;
   t.x = m % p.d3;
   t.b = m / p.d3;
@@ -50,33 +55,36 @@ __device__ __forceinline__ HaloTile halo_decode(const HaloParams& p, int tile, i
   return t;
 }
 
-__device__ __forceinline__ uint64_t halo_desc_a(uint32_t saddr, int base_offset_mode) {
+__device__ __forceinline__ uint64_t halo_desc_a(uint32_t saddr, int base_offset_mode, int hz) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)((HALO_Z * 128) >> 4) << 32;  // 8-row groups are one halo line (10 rows) apart
+  d |= (uint64_t)((hz * 128) >> 4) << 32;  // 8-row groups are one halo line (10 or 18 rows) apart
   d |= (uint64_t)1 << 46;
   if (base_offset_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;
   d |= (uint64_t)2 << 61;
   return d;
 }
 
-template <int BN, int SA, int SB, int CTAS_PER_SM>
+template <int BN, int SA, int SB, int CTAS_PER_SM, int ZT>
 __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                       const __grid_constant__ CUtensorMap tmB,
                                                                       const __grid_constant__ CUtensorMap tmC,
                                                                       const HaloParams p) {
   constexpr int B_STAGE_BYTES = BN * 128;
   constexpr int SLABS = BN / 64;
-  constexpr int TMEM_COLS = 2 * BN;
+  constexpr int TMEM_COLS = 2 * ZT * BN;   // two accumulator slots, ZT tiles each
   constexpr uint32_t IDESC = umma_idesc_bf16(128, BN);
+  constexpr int HALO_Z = halo_z(ZT);
+  constexpr int HALO_A_BYTES = halo_a_bytes(ZT);
+  constexpr int HALO_A_STAGE = halo_a_stage(ZT);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + SA * HALO_A_STAGE;
   uint8_t* smem_c = smem_b + SB * B_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + SLABS * HALO_SLAB_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + ZT * SLABS * HALO_SLAB_BYTES);
   uint64_t* full_a = bars;
   uint64_t* empty_a = bars + SA;
   uint64_t* full_b = bars + 2 * SA;
@@ -114,7 +122,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_kernel(const __gr
     if (lane == 0) {
       uint32_t ia = 0, ib = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const HaloTile t = halo_decode(p, tile, BN);
+        const HaloTile t = halo_decode(p, tile, BN, 8 * ZT);
         for (int t3 = 0; t3 < 3; ++t3) {
           for (int cb = 0; cb < p.cblocks; ++cb) {
             {
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_kernel(const __gr
         const int slot = lt & 1;
         mbar_wait(smem_u32(&bar_tempty[slot]), ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t acc = tmem_base + (uint32_t)(slot * BN);
+        const uint32_t acc = tmem_base + (uint32_t)(slot * ZT * BN);
         uint32_t first = 1;
         for (int t3 = 0; t3 < 3; ++t3) {
           for (int cb = 0; cb < p.cblocks; ++cb) {
@@ -161,11 +169,14 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_kernel(const __gr
                 const int sb = ib % SB;
                 mbar_wait(smem_u32(&full_b[sb]), (ib / SB) & 1);
                 tc_fence_after();
-                const uint64_t da = halo_desc_a(a_base + (uint32_t)((t2 * HALO_Z + t1) * 128), p.base_offset_mode);
                 const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + sb * B_STAGE_BYTES));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (k < p.ksteps) umma_bf16(acc, da + 2 * k, db + 2 * k, IDESC, (first && k == 0) ? 0u : 1u);
+                for (int h = 0; h < ZT; ++h) {   // the z-adjacent tiles: same weights, views 8 halo rows apart
+                  const uint64_t da = halo_desc_a(a_base + (uint32_t)((t2 * HALO_Z + t1 + 8 * h) * 128), p.base_offset_mode, HALO_Z);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    if (k < p.ksteps) umma_bf16(acc + (uint32_t)(h * BN), da + 2 * k, db + 2 * k, IDESC, (first && k == 0) ? 0u : 1u);
+                  }
                 }
                 first = 0;
                 umma_commit(smem_u32(&empty_b[sb]));
@@ -208,89 +219,99 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_kernel(const __gr
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const int slot = lt & 1;
-      const HaloTile t = halo_decode(p, tile, BN);
-      const bool valid = (t.z0 + i1 < p.d1) && (t.y0 + i2 < p.d2);
+      const HaloTile t = halo_decode(p, tile, BN, 8 * ZT);
       mbar_wait(smem_u32(&bar_tfull[slot]), (lt >> 1) & 1);
       tc_fence_after();
-      // the staging tile must have been read by the previous TMA store; the statistics scratch must be free
-      if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      named_bar_sync(1, 128);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t raw[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN + c0), raw);
-        tmem_ld_wait();
-        if (p.residual != nullptr && valid) {
-          // out = acc + residual (the input-gradient convolution adding to a gradient that has already arrived)
-          const long long row = (((long long)t.b * p.d3 + t.x) * p.d2 + (t.y0 + i2)) * p.d1 + (t.z0 + i1);
-          const __nv_bfloat16* rp = p.residual + row * p.ldr + p.res_col0 + t.n0 + c0;
+      for (int h = 0; h < ZT; ++h) {   // the z-adjacent 128-voxel tiles of this CTA tile, one staging buffer each
+        const int zt0 = t.z0 + 8 * h;
+        const bool valid = (zt0 + i1 < p.d1) && (t.y0 + i2 < p.d2);
+        uint8_t* cbuf = smem_c + (size_t)h * SLABS * HALO_SLAB_BYTES;
+        // this staging buffer must have been read by its previous TMA store; the statistics scratch must be free
+        if (e == 0) {
+          if (ZT > 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        named_bar_sync(1, 128);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((slot * ZT + h) * BN + c0), raw);
+          tmem_ld_wait();
+          if (p.residual != nullptr && valid) {
+            // out = acc + residual (the input-gradient convolution adding to a gradient that has already arrived)
+            const long long row = (((long long)t.b * p.d3 + t.x) * p.d2 + (t.y0 + i2)) * p.d1 + (zt0 + i1);
+            const __nv_bfloat16* rp = p.residual + row * p.ldr + p.res_col0 + t.n0 + c0;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(rp + j);
-            float2 f;
-            f = unpack_bf16x2(rv.x); raw[j] = __float_as_uint(__uint_as_float(raw[j]) + f.x); raw[j + 1] = __float_as_uint(__uint_as_float(raw[j + 1]) + f.y);
-            f = unpack_bf16x2(rv.y); raw[j + 2] = __float_as_uint(__uint_as_float(raw[j + 2]) + f.x); raw[j + 3] = __float_as_uint(__uint_as_float(raw[j + 3]) + f.y);
-            f = unpack_bf16x2(rv.z); raw[j + 4] = __float_as_uint(__uint_as_float(raw[j + 4]) + f.x); raw[j + 5] = __float_as_uint(__uint_as_float(raw[j + 5]) + f.y);
-            f = unpack_bf16x2(rv.w); raw[j + 6] = __float_as_uint(__uint_as_float(raw[j + 6]) + f.x); raw[j + 7] = __float_as_uint(__uint_as_float(raw[j + 7]) + f.y);
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(rp + j);
+              float2 f;
+              f = unpack_bf16x2(rv.x); raw[j] = __float_as_uint(__uint_as_float(raw[j]) + f.x); raw[j + 1] = __float_as_uint(__uint_as_float(raw[j + 1]) + f.y);
+              f = unpack_bf16x2(rv.y); raw[j + 2] = __float_as_uint(__uint_as_float(raw[j + 2]) + f.x); raw[j + 3] = __float_as_uint(__uint_as_float(raw[j + 3]) + f.y);
+              f = unpack_bf16x2(rv.z); raw[j + 4] = __float_as_uint(__uint_as_float(raw[j + 4]) + f.x); raw[j + 5] = __float_as_uint(__uint_as_float(raw[j + 5]) + f.y);
+              f = unpack_bf16x2(rv.w); raw[j + 6] = __float_as_uint(__uint_as_float(raw[j + 6]) + f.x); raw[j + 7] = __float_as_uint(__uint_as_float(raw[j + 7]) + f.y);
+            }
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
+          const uint32_t base = smem_u32(cbuf) + (uint32_t)((c0 >> 6) * HALO_SLAB_BYTES + r * 128);
+          const int cbk = (c0 & 63) >> 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t addr = base + (uint32_t)(((cbk + i) ^ (r & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
+                         "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                         : "memory");
+          }
+          if (p.stats != nullptr) {
+            float v[32], sq[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 f = unpack_bf16x2(pk[j]);
+              v[2 * j] = valid ? f.x : 0.f;
+              v[2 * j + 1] = valid ? f.y : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+            const float s_sum = warp_transpose_reduce(v, lane);
+            const float s_sq = warp_transpose_reduce(sq, lane);
+            stat_scratch[q * BN + c0 + lane] = make_float2(s_sum, s_sq);
           }
         }
-        uint32_t pk[16];
+        if (h == ZT - 1) {   // both halves of the accumulator slot have been read
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[slot]));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        named_bar_sync(2, 128);
+        if (e == 0) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
-        const uint32_t base = smem_u32(smem_c) + (uint32_t)((c0 >> 6) * HALO_SLAB_BYTES + r * 128);
-        const int cbk = (c0 & 63) >> 3;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t addr = base + (uint32_t)(((cbk + i) ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
-                       "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
-                       : "memory");
+          for (int sl = 0; sl < SLABS; ++sl) {
+            if (t.n0 + sl * 64 < p.n_real) {
+              asm volatile(
+                  "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(&tmC),
+                  "r"(smem_u32(cbuf + sl * HALO_SLAB_BYTES)), "r"(t.n0 + sl * 64), "r"(zt0), "r"(t.y0), "r"(t.x), "r"(t.b)
+                  : "memory");
+            }
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (p.stats != nullptr) {
-          float v[32], sq[32];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 f = unpack_bf16x2(pk[j]);
-            v[2 * j] = valid ? f.x : 0.f;
-            v[2 * j + 1] = valid ? f.y : 0.f;
+          if (t.b != stat_batch) {
+            flush_stats(stat_batch);
+            stat_batch = t.b;
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-          const float s_sum = warp_transpose_reduce(v, lane);
-          const float s_sq = warp_transpose_reduce(sq, lane);
-          stat_scratch[q * BN + c0 + lane] = make_float2(s_sum, s_sq);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[slot]));
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      named_bar_sync(2, 128);
-      if (e == 0) {
-#pragma unroll
-        for (int sl = 0; sl < SLABS; ++sl) {
-          if (t.n0 + sl * 64 < p.n_real) {
-            asm volatile(
-                "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(&tmC),
-                "r"(smem_u32(smem_c + sl * HALO_SLAB_BYTES)), "r"(t.n0 + sl * 64), "r"(t.z0), "r"(t.y0), "r"(t.x), "r"(t.b)
-                : "memory");
-          }
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-      if (p.stats != nullptr) {
-        if (t.b != stat_batch) {
-          flush_stats(stat_batch);
-          stat_batch = t.b;
-        }
-#pragma unroll
-        for (int k = 0; k < STAT_PER_THREAD; ++k) {
-          const int c = e + 128 * k;
-          if (c < BN) {
-            const float2 s0 = stat_scratch[c], s1 = stat_scratch[BN + c], s2 = stat_scratch[2 * BN + c],
-                         s3 = stat_scratch[3 * BN + c];
-            acc_s[k] += (s0.x + s1.x) + (s2.x + s3.x);
-            acc_q[k] += (s0.y + s1.y) + (s2.y + s3.y);
+          for (int k = 0; k < STAT_PER_THREAD; ++k) {
+            const int c = e + 128 * k;
+            if (c < BN) {
+              const float2 s0 = stat_scratch[c], s1 = stat_scratch[BN + c], s2 = stat_scratch[2 * BN + c],
+                           s3 = stat_scratch[3 * BN + c];
+              acc_s[k] += (s0.x + s1.x) + (s2.x + s3.x);
+              acc_q[k] += (s0.y + s1.y) + (s2.y + s3.y);
+            }
           }
         }
       }
@@ -313,16 +334,16 @@ static int halo_sm_count() {
   return n;
 }
 
-template <int BN, int SA, int SB, int CTAS_PER_SM>
+template <int BN, int SA, int SB, int CTAS_PER_SM, int ZT = 1>
 static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const HaloParams& p,
                        cudaStream_t stream) {
-  constexpr int smem = 1024 + SA * HALO_A_STAGE + SB * BN * 128 + (BN / 64) * HALO_SLAB_BYTES + (2 * SA + 2 * SB + 4) * 8 +
-                       16 + 4 * BN * 8;
+  constexpr int smem = 1024 + SA * halo_a_stage(ZT) + SB * BN * 128 + ZT * (BN / 64) * HALO_SLAB_BYTES +
+                       (2 * SA + 2 * SB + 4) * 8 + 16 + 4 * BN * 8;
   static_assert(CTAS_PER_SM * (smem + 1024) <= 228 * 1024, "shared memory budget");
-  static_assert(CTAS_PER_SM * 2 * BN <= 512, "TMEM budget");
+  static_assert(CTAS_PER_SM * 2 * ZT * BN <= 512, "TMEM budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv3_halo_kernel<BN, SA, SB, CTAS_PER_SM>,
+    cudaError_t e = cudaFuncSetAttribute(conv3_halo_kernel<BN, SA, SB, CTAS_PER_SM, ZT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
@@ -330,7 +351,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   int cap = persistent_sms(halo_sm_count()) * CTAS_PER_SM;
   if (cap > p.n_tiles) cap -= cap % p.n_tiles;
   const int grid = p.total_tiles < cap ? p.total_tiles : cap;
-  const cudaError_t le = launch_pdl(conv3_halo_kernel<BN, SA, SB, CTAS_PER_SM>, dim3(grid), dim3(192), smem, stream, tmA, tmB, tmC, p);
+  const cudaError_t le = launch_pdl(conv3_halo_kernel<BN, SA, SB, CTAS_PER_SM, ZT>, dim3(grid), dim3(192), smem, stream, tmA, tmB, tmC, p);
   count_launch();
   return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
@@ -350,6 +371,14 @@ int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
   if (d->d1 % 8 != 0 || d->d2 % 16 != 0 || d->a_c % 64 != 0 || d->n_real % 64 != 0) return CTU_E_UNSUPPORTED;
   if (!tma_encoder()) return CTU_E_DRIVER;
   const CUtensorMapL2promotion l2p = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  static const int variant = [] { const char* e = getenv("CTU_CONV_HALO_VARIANT"); return e ? atoi(e) : 0; }();
+  // CTU_CONV_HALO_VARIANT=3: two z-adjacent tiles per CTA sharing one weight stream (64-output-channel layers).  Measured
+  // on B200 (profiles/r02_halo_zt2.txt): 64->64 @96^3 0.402 vs 0.398 ms, 128->64 0.760 vs 0.740, 64->64 @48x48x96 0.113 vs
+  // 0.118 — halving the weight traffic changes nothing, i.e. these layers are NOT bound by L2 -> shared-memory traffic
+  // but by the tensor pipe's shared-memory operand feed at N = 64 (each M128 x N64 x K16 instruction re-reads its 4 KB A
+  // tile + 2 KB B tile: 6 KB per 32 tensor-pipe cycles > 128 B/clk), a ceiling of ~2/3 of the N >= 128 rate.  Off by
+  // default.
+  const int zt = (d->block_n == 64 && d->d1 % 16 == 0 && variant == 3) ? 2 : 1;
   CUtensorMap tmA, tmB, tmC;
   {
     cuuint64_t dims[5] = {(cuuint64_t)d->a_c, (cuuint64_t)d->d1, (cuuint64_t)d->d2, (cuuint64_t)d->d3, (cuuint64_t)d->d4};
@@ -358,7 +387,7 @@ int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
     strides[1] = strides[0] * d->d1;
     strides[2] = strides[1] * d->d2;
     strides[3] = strides[2] * d->d3;
-    cuuint32_t box[5] = {64, HALO_Z, HALO_Y, 1, 1};
+    cuuint32_t box[5] = {64, (cuuint32_t)halo_z(zt), HALO_Y, 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     if (tma_encoder()(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->a), dims, strides, box, es,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
@@ -390,7 +419,7 @@ int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
       return CTU_E_DRIVER;
   }
   HaloParams p;
-  p.T1 = d->d1 / 8;
+  p.T1 = d->d1 / (8 * zt);
   p.T2 = d->d2 / 16;
   p.d1 = d->d1; p.d2 = d->d2; p.d3 = d->d3; p.d4 = d->d4;
   p.n_tiles = d->n_pad / d->block_n;
@@ -404,10 +433,10 @@ int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
   const long long tiles = (long long)p.T1 * p.T2 * d->d3 * d->d4 * p.n_tiles;
   if (tiles <= 0 || tiles > 0x7fffffffLL) return CTU_E_BADARG;
   p.total_tiles = (int)tiles;
-  static const int variant = [] { const char* e = getenv("CTU_CONV_HALO_VARIANT"); return e ? atoi(e) : 0; }();
   // several small CTAs per SM (one halo stage each) beat fewer CTAs with deeper rings: 3 x <64,1,4> reaches 1008
   // TFLOP/s where 2 x <64,2,5> reaches 895 and 1 x <64,3,8> 483
   if (d->block_n == 64) {
+    if (zt == 2) return launch_halo<64, 1, 4, 2, 2>(tmA, tmB, tmC, p, stream);
     if (variant == 2) return launch_halo<64, 2, 5, 2>(tmA, tmB, tmC, p, stream);
     return launch_halo<64, 1, 4, 3>(tmA, tmB, tmC, p, stream);
   }

@@ -48,6 +48,68 @@ class GradientAllReduce:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
             flat.mul_(1.0 / dist.get_world_size(self.group))
 
+    def reduce_and_step(self, optimizer, chunks: int = 4) -> int:
+        """All-reduce (mean) + optimizer update, pipelined: the flat gradient buffer is exchanged in `chunks` pieces cut
+        at parameter boundaries; all pieces are queued on NCCL's stream at once and the parameters of piece i are updated
+        (optimizer.step(only=...), hybrid_ctunet_b200.optim.AdamW) as soon as piece i has arrived, while piece i+1 is
+        still on the wire.  The update of a parameter reads nothing but its own gradient, so the result equals
+        reduce() followed by optimizer.step().  Optimizers without `only=` get the plain sequence."""
+        import inspect
+        can_subset = "only" in inspect.signature(optimizer.step).parameters
+        with_grad = [p for p in self.params if p.grad is not None]
+        if not with_grad:
+            return 0
+        by_storage = {}
+        for p in with_grad:
+            by_storage.setdefault(p.grad.untyped_storage().data_ptr(), []).append(p)
+        main = max(by_storage.values(), key=lambda ps: sum(p.grad.numel() for p in ps))
+        span = self._span_view([p.grad for p in main]) if len(main) > 1 else None
+        if span is None or not can_subset or chunks <= 1:
+            n = self.reduce()
+            optimizer.step()
+            return n
+        # pieces of the flat span cut at gradient boundaries, about equal in bytes
+        main = sorted(main, key=lambda p: p.grad.storage_offset())
+        lo = span.storage_offset()
+        total = span.numel()
+        pieces, cur, start = [], [], lo
+        for p in main:
+            cur.append(p)
+            end = p.grad.storage_offset() + p.grad.numel()
+            if end - start >= total / chunks and len(pieces) < chunks - 1:
+                pieces.append((start, end, cur))
+                cur, start = [], end
+        if cur:
+            pieces.append((start, lo + total, cur))
+        st = span.untyped_storage()
+        nccl = dist.get_backend(self.group) == "nccl"
+        works, views = [], []
+        for a, b, _ in pieces:
+            view = torch.empty(0, dtype=torch.float32, device=span.device).set_(st, a, (b - a,))
+            views.append(view)
+            works.append(dist.all_reduce(view, op=dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM, group=self.group,
+                                         async_op=True))
+        main_ids = {id(p) for p in main}
+        rest = [p for p in with_grad if id(p) not in main_ids]
+        for i, ((_, _, ps), wk) in enumerate(zip(pieces, works)):
+            wk.wait()                                   # the current stream waits for piece i only
+            if not nccl:
+                views[i].mul_(1.0 / dist.get_world_size(self.group))
+            optimizer.step(only=ps, key=("dp", i, len(pieces)))
+        if rest:                                        # gradients living outside the flat buffer (relative-position tables)
+            m = sum(p.grad.numel() for p in rest)
+            if self._flat is None or self._flat.numel() != m or self._flat.device != rest[0].grad.device:
+                self._flat = torch.empty(m, dtype=torch.float32, device=rest[0].grad.device)
+            views, off = [], 0
+            for p in rest:
+                views.append(self._flat[off:off + p.grad.numel()].view(p.grad.shape))
+                off += p.grad.numel()
+            torch._foreach_copy_(views, [p.grad for p in rest])
+            self._all_reduce_mean(self._flat)
+            torch._foreach_copy_([p.grad for p in rest], views)
+            optimizer.step(only=rest, key=("dp", "rest"))
+        return sum(p.grad.numel() for p in with_grad)
+
     def reduce(self) -> int:
         """Average the existing .grad tensors over the group in place; returns the number of elements exchanged."""
         grads = [p.grad for p in self.params if p.grad is not None]

@@ -59,16 +59,20 @@ class AdamW(torch.optim.Optimizer):
         return table, unit
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, only=None, key=None):
+        """`only` (optional): restrict the update to these parameters — the data-parallel step updates the parameters of
+        one all-reduced gradient chunk while the next chunk is still on the wire (dp.GradientAllReduce.reduce_and_step);
+        `key` names the subset for the cached device table."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
         lib = _lib.require_device()
+        subset = None if only is None else {id(p) for p in only}
         for gi, group in enumerate(self.param_groups):
             buckets = {}  # step count -> [(p, grad, exp_avg, exp_avg_sq)]: one launch per distinct count (normally one)
             for p in group["params"]:
-                if p.grad is None:
+                if p.grad is None or (subset is not None and id(p) not in subset):
                     continue
                 if not p.is_cuda or p.dtype != torch.float32 or p.grad.dtype != torch.float32 or p.grad.is_sparse:
                     raise RuntimeError("ctunet_b200 AdamW: CUDA fp32 dense parameters and gradients only (no CPU fallback)")
@@ -85,7 +89,7 @@ class AdamW(torch.optim.Optimizer):
                 continue
             b1, b2 = group["betas"]
             for s, ent in buckets.items():
-                table, units = self._table(gi, ent, cache=len(buckets) == 1)
+                table, units = self._table((gi, key), ent, cache=len(buckets) == 1)
                 stream = torch.cuda.current_stream(ent[0][0].device).cuda_stream
                 check(lib.ctu_adamw_step(table.data_ptr(), len(ent), units, float(group["lr"]), float(b1), float(b2),
                                          float(group["eps"]), float(group["weight_decay"]), int(s), stream),

@@ -94,3 +94,53 @@ def test_window_sharding_covers_every_window_once():
     out = _run(_shard_case)
     assert out[0][0] == 500 and out[0][3] and out[1][3]
     assert out[0][1:3] == (0, 250) and out[1][1:3] == (250, 500)
+
+
+class _SubsetSGD(torch.optim.SGD):
+    """SGD with the `only=` / `key=` arguments of hybrid_ctunet_b200.optim.AdamW.step (CPU stand-in)."""
+
+    @torch.no_grad()
+    def step(self, closure=None, only=None, key=None):
+        keep = None if only is None else {id(p) for p in only}
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is not None and (keep is None or id(p) in keep):
+                    p.add_(p.grad, alpha=-group["lr"])
+
+
+def _pipelined_case(rank, world):
+    """reduce_and_step == reduce() then step(): gradients are slices of one flat buffer (+ one that lives elsewhere, + a
+    parameter without gradient), exchanged in 3 pieces with the update of piece i issued while piece i+1 is in flight."""
+    from hybrid_ctunet_b200.dp import GradientAllReduce
+    shapes = [(3, 5), (7,), (2, 2), (4, 4), (9,), (6,)]
+
+    def build():
+        torch.manual_seed(0)
+        params = [torch.nn.Parameter(torch.randn(*s)) for s in shapes] + [torch.nn.Parameter(torch.randn(3))]
+        flat = torch.full((64,), float("nan"))
+        off = 0
+        for i, p in enumerate(params[:5]):
+            n = p.numel()
+            v = flat[off:off + n].view(p.shape)
+            v.copy_(torch.arange(n, dtype=torch.float32).reshape(p.shape) * (rank + 1) + i)
+            p.grad = v
+            off += -(-n // 4) * 4
+        params[5].grad = torch.full((6,), float(rank + 1))      # a gradient outside the flat buffer
+        return params                                            # params[6]: no gradient at all
+    a, b = build(), build()
+    GradientAllReduce(a).reduce_and_step(_SubsetSGD(a, lr=0.5), chunks=3)
+    ar = GradientAllReduce(b)
+    ar.reduce()
+    _SubsetSGD(b, lr=0.5).step()
+    return [p.detach().clone() for p in a], [p.detach().clone() for p in b], [None if p.grad is None else p.grad.clone() for p in a]
+
+
+def test_pipelined_allreduce_and_step_equals_sequential():
+    out = _run(_pipelined_case)
+    for rank in (0, 1):
+        pa, pb, grads = out[rank]
+        for x, y in zip(pa, pb):
+            assert torch.equal(x, y)
+        assert grads[6] is None and torch.equal(grads[5], torch.full((6,), 1.5))
+    for x, y in zip(out[0][0], out[1][0]):
+        assert torch.equal(x, y)          # both ranks hold the same parameters after the step

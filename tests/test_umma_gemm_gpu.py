@@ -104,7 +104,8 @@ def _pack_conv3(w):  # [Cout, Cin, kX, kY, kZ] -> [Cout, 27*Cin] (tap-major, cha
 
 @pytest.mark.parametrize("B,X,Y,Z,Cin,Cout,bn", [(1, 8, 8, 32, 64, 64, 64), (2, 6, 6, 12, 128, 128, 128),
                                                   (1, 12, 12, 24, 64, 128, 64), (1, 24, 24, 48, 128, 64, 64),
-                                                  (1, 5, 7, 9, 64, 64, 64), (1, 96, 96, 96, 64, 64, 64)])
+                                                  (1, 5, 7, 9, 64, 64, 64), (1, 96, 96, 96, 64, 64, 64),
+                                                  (2, 3, 32, 32, 128, 64, 64), (1, 4, 16, 48, 64, 64, 64)])
 def test_conv3x3x3(B, X, Y, Z, Cin, Cout, bn):
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(X * Y + Cin)
@@ -122,6 +123,31 @@ def test_conv3x3x3(B, X, Y, Z, Cin, Cout, bn):
     o = out.double().reshape(B, -1, Cout)
     assert torch.allclose(stats[..., 0], o.sum(1), rtol=1e-6, atol=1e-3)
     assert torch.allclose(stats[..., 1], (o * o).sum(1), rtol=1e-6, atol=1e-3)
+
+
+def test_conv3x3x3_skips_zero_padded_channels():
+    """ResNet layer-1 shape class: 32 live channels in 64-channel rows (resnet.py:181-186).  With a_c_live = 32 the halo
+    kernel issues half of the K steps; the result must equal the full-K result exactly (the skipped products are 0)."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, X, Y, Z = 1, 6, 16, 32
+    a = torch.randn(B, X, Y, Z, 64, device="cuda", generator=g).to(torch.bfloat16)
+    a[..., 32:] = 0
+    w = torch.randn(64, 64, 3, 3, 3, device="cuda", generator=g) / (27 * 32) ** 0.5
+    w[32:] = 0
+    w[:, 32:] = 0
+    outs = []
+    for live in (0, 32):
+        pw = ops.pack_matrix(_pack_conv3(w), ksize=3, a_c=64, block_n=64)
+        pw.a_c_live = live
+        out = torch.full((B, X, Y, Z, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+        stats = torch.zeros(B, 64, 2, device="cuda", dtype=torch.float64)
+        ops.gemm(a, pw, out, dims=(Z, Y, X, B), stats=stats)
+        outs.append((out, stats))
+    ref = F.conv3d(a.float().permute(0, 4, 1, 2, 3), w.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 4, 1)
+    assert _rel(outs[0][0].float(), ref) < 2 ** -8
+    assert torch.equal(outs[0][0], outs[1][0]) and float(outs[1][0][..., 32:].abs().max()) == 0.0
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-9, atol=1e-6)
 
 
 @pytest.mark.parametrize("B,X,Y,Z,Cin,Cout,bn", [(1, 8, 16, 32, 64, 64, 64), (2, 6, 32, 16, 128, 128, 128),
