@@ -652,6 +652,10 @@ def main():
         classes = head["classes"]
         roofline = None
         if classes:
+            for c in classes:   # DRAM traffic of the class's representative kernel from the committed ncu --set full capture
+                tb, src = _traffic_for(c["class"])
+                if tb is not None:
+                    c["traffic"], c["traffic_source"] = tb, src
             top = dict(classes[0])
             traffic, tsrc = _traffic_for(top["class"])
             roofline = {"bound": top["bound"], "kernel": top["class"], "achieved": top["achieved"], "peak": top["peak"],

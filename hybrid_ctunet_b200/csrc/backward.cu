@@ -484,8 +484,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 #pragma unroll
   for (int j = 0; j < V; ++j) acc[j] = 0.f;
   if (cvec < nvec) {
-    // four rows per iteration, every load issued before the first add
-    constexpr int UNR = 4;
+    // eight rows per iteration, every load issued before the first add
+    constexpr int UNR = 8;
     const long long stride = (long long)gridDim.y * RL;
     for (long long r0 = (long long)blockIdx.y * RL + rl; r0 < M; r0 += stride * UNR) {
       uint4 q[UNR];
@@ -904,8 +904,8 @@ extern "C" int ctu_colsum(const void* x, int x_is_f32, long long ldx, long long 
   const long long gx = (nvec + cw - 1) / cw;
   if (gx > 0x7fffffffLL) return CTU_E_BADARG;
   const int rl = 256 / cw;
-  long long gy = (M + rl * 16 - 1) / (rl * 16);
-  const long long cap = ((long long)bw_num_sms() * 16 + gx - 1) / gx;
+  long long gy = (M + rl * 32 - 1) / (rl * 32);
+  const long long cap = ((long long)bw_num_sms() * 8 + gx - 1) / gx;   // ~8 blocks per SM: each ends with one atomic per column
   if (gy > cap) gy = cap;
   if (gy > 65535) gy = 65535;
   if (gy < 1) gy = 1;

@@ -68,3 +68,31 @@ def test_matches_reference_keys_shapes_and_seeded_init(which):
     for k in r:
         assert r[k].shape == m[k].shape, k
         assert torch.equal(r[k], m[k]), k
+
+
+def test_dropin_install_serves_the_reference_module_names():
+    """`from networks.hybrid_CTUNet import CTUNet` (main_CTUNet.py:21) resolves to the drop-in after dropin.install()."""
+    import importlib
+    import sys
+    import hybrid_ctunet_b200.dropin as dropin
+    saved_path, saved_mods = list(sys.path), {k: v for k, v in sys.modules.items() if k == "networks" or k.startswith("networks.")}
+    try:
+        dropin.install()
+        hyb = importlib.import_module("networks.hybrid_CTUNet")
+        res = importlib.import_module("networks.resnet")
+        vit = importlib.import_module("networks.vit")
+        from hybrid_ctunet_b200.networks import hybrid_CTUNet as ours
+        assert hyb.CTUNet is ours.CTUNet and hyb.TUNet is ours.TUNet and hyb.CUNet is ours.CUNet
+        assert callable(res.generate_model) and hasattr(vit, "ViT")
+        fake = type(sys)("trainer_CTUNet")
+        fake.sliding_window_inference = lambda *a, **k: None
+        sys.modules["trainer_CTUNet"] = fake
+        assert dropin.patch_trainers() == ["trainer_CTUNet"]
+        from hybrid_ctunet_b200.trainer_CTUNet import sliding_window_inference
+        assert fake.sliding_window_inference is sliding_window_inference
+    finally:
+        sys.modules.pop("trainer_CTUNet", None)
+        for k in [k for k in sys.modules if k == "networks" or k.startswith("networks.")]:
+            del sys.modules[k]
+        sys.modules.update(saved_mods)
+        sys.path[:] = saved_path

@@ -16,7 +16,8 @@ CLASSES = [("tcgen05 conv/gemm/dgrad", ("umma_gemm_kernel", "conv3_halo_kernel")
            ("InstanceNorm", ("in_",)), ("attention", ("attention",)), ("LayerNorm", ("layernorm", "patchify")),
            ("pack/unpack/AdamW", ("pack_weights", "unpack_grads", "adamw")), ("gelu/pwa", ("gelu", "pwa_")),
            ("loss", ("dice_ce",)),
-           ("colsum/accumulate/cast/layout", ("colsum", "accumulate", "cast_", "space_to_depth", "cf_to_cl", "subsample", "im2col", "conv_cin1"))]
+           ("colsum/accumulate/cast/layout", ("colsum", "accumulate", "cast_", "space_to_depth", "cf_to_cl", "subsample", "im2col", "conv_cin1")),
+           ("head backward (fused CUDA-core)", ("head_bwd",))]
 cl = collections.OrderedDict((c, 0.0) for c, _ in CLASSES)
 cl["torch (loss glue, fills, copies)"] = 0.0
 agg = collections.OrderedDict()
