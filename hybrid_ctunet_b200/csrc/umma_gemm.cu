@@ -48,6 +48,7 @@ struct GemmParams {
   int convt_cout, u1, u2, u3;
   int stats_ld, out_col0;
   int tma_store;
+  int fast;  // bf16 rows through the TMA store, no activation, no or bf16 residual: the epilogue takes the lean chunk
 };
 
 struct TileCoord {
@@ -70,6 +71,40 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
   c.n0 = n_tile * bn;
   return c;
 }
+
+// The tiles of a persistent CTA are `step` apart (the grid size, a multiple of n_tiles): instead of eight integer divisions
+// per tile and thread (decode_tile), the coordinates are advanced by the decomposed step with one carry per dimension.
+struct TileWalker {
+  int t1, t2, t3, t4, n0;
+  int s1, s2, s3, s4;
+  __device__ __forceinline__ void init(const GemmParams& p, int tile0, int step, int bn) {
+    n0 = (tile0 % p.n_tiles) * bn;
+    int m = tile0 / p.n_tiles;
+    t1 = m % p.T1; m /= p.T1;
+    t2 = m % p.T2; m /= p.T2;
+    t3 = m % p.T3;
+    t4 = m / p.T3;
+    int sm = step / p.n_tiles;   // (step % n_tiles == 0, or the CTA has a single tile)
+    s1 = sm % p.T1; sm /= p.T1;
+    s2 = sm % p.T2; sm /= p.T2;
+    s3 = sm % p.T3;
+    s4 = sm / p.T3;
+  }
+  __device__ __forceinline__ void next(const GemmParams& p) {
+    t1 += s1;
+    if (t1 >= p.T1) { t1 -= p.T1; ++t2; }
+    t2 += s2;
+    if (t2 >= p.T2) { t2 -= p.T2; ++t3; }
+    t3 += s3;
+    if (t3 >= p.T3) { t3 -= p.T3; ++t4; }
+    t4 += s4;
+  }
+  __device__ __forceinline__ TileCoord coord(const GemmParams& p) const {
+    TileCoord c;
+    c.x1 = t1 * p.b1; c.x2 = t2 * p.b2; c.x3 = t3 * p.b3; c.t4 = t4; c.n0 = n0;
+    return c;
+  }
+};
 
 // Exact-form GELU 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7, far
 // below the bf16 rounding of the stored result): ~15 instructions instead of erff's ~50, the epilogue of the FFN
@@ -163,8 +198,10 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, CTAS_PER_SM) umma_gemm_ke
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile, BN);
+      TileWalker tw;
+      tw.init(p, blockIdx.x, gridDim.x, BN);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, tw.next(p)) {
+        const TileCoord tc = tw.coord(p);
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -248,10 +285,12 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, CTAS_PER_SM) umma_gemm_ke
     };
 
     int lt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+    TileWalker tw;
+    tw.init(p, blockIdx.x, gridDim.x, BN);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt, tw.next(p)) {
       const int slot = lt & 1;
       const uint32_t uph = (lt >> 1) & 1;
-      const TileCoord tc = decode_tile(p, tile, BN);
+      const TileCoord tc = tw.coord(p);
       const int n0 = tc.n0;
       const int v1 = tc.x1 + i1, v2 = tc.x2 + i2, v3 = tc.x3 + i3;
       const bool valid = (v1 < p.d1) && (v2 < p.d2) && (v3 < p.d3);
@@ -419,10 +458,66 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, CTAS_PER_SM) umma_gemm_ke
           if (lane < CH) stat_scratch[q * BN + c0 + lane] = make_float2(s_sum, s_sq);
         }
       };
+      if constexpr (CH == 32 && SLABS > 0) {
+        if (p.fast) {
+          // bf16 rows through the staging tile, no activation, no residual (the 1x1x1 convolutions, qkv / output
+          // projections, FFN up-projection of the training forward): nothing but TMEM load, optional bias, pack, store
+          const bool zero_row = col_stats && !valid;   // rows outside the volume must not count in the statistics
 #pragma unroll 1
-      for (int c0 = col_lo; c0 < col_lo + COLS_PER_WARP; c0 += CH) {
-        if (n0 + c0 + CH <= p.n_real) chunk(c0, std::true_type{});
-        else chunk(c0, std::false_type{});
+          for (int c0 = col_lo; c0 < col_lo + COLS_PER_WARP; c0 += 32) {
+            uint32_t raw[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * BN + c0), raw);
+            tmem_ld_wait();
+            if (p.bias != nullptr) {
+              const float4* bp = reinterpret_cast<const float4*>(bias_s + c0);
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bv = bp[j >> 2];
+                raw[j] = __float_as_uint(__uint_as_float(raw[j]) + bv.x);
+                raw[j + 1] = __float_as_uint(__uint_as_float(raw[j + 1]) + bv.y);
+                raw[j + 2] = __float_as_uint(__uint_as_float(raw[j + 2]) + bv.z);
+                raw[j + 3] = __float_as_uint(__uint_as_float(raw[j + 3]) + bv.w);
+              }
+            }
+            if (p.res_mode == CTU_RES_BF16 && valid) {   // (the input-gradient GEMM adding to a gradient already there)
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                                               out_row * p.ldr + p.out_col0 + colbase + c0);
+              uint4 rv[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) rv[i] = rp[i];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t u[4] = {rv[i].x, rv[i].y, rv[i].z, rv[i].w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  const float2 f = unpack_bf16x2(u[h]);
+                  raw[8 * i + 2 * h] = __float_as_uint(__uint_as_float(raw[8 * i + 2 * h]) + f.x);
+                  raw[8 * i + 2 * h + 1] = __float_as_uint(__uint_as_float(raw[8 * i + 2 * h + 1]) + f.y);
+                }
+              }
+            }
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              pk[j] = zero_row ? 0u : pack_bf16x2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
+            const uint32_t base = smem_u32(cbuf) + (uint32_t)((c0 >> 6) * SLAB_BYTES + r * 128);
+            const int cb = (c0 & 63) >> 3;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t addr = base + (uint32_t)(((cb + i) ^ (r & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
+                           "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                           : "memory");
+            }
+          }
+        }
+      }
+      if (!(CH == 32 && SLABS > 0) || !p.fast) {
+#pragma unroll 1
+        for (int c0 = col_lo; c0 < col_lo + COLS_PER_WARP; c0 += CH) {
+          if (n0 + c0 + CH <= p.n_real) chunk(c0, std::true_type{});
+          else chunk(c0, std::false_type{});
+        }
       }
 
       // accumulator fully read: hand it back to the MMA warp before the (slower) global write-back
@@ -553,6 +648,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   int cap = persistent_sms(sm_count()) * CTAS_PER_SM;
   if (cap > p.n_tiles) cap -= cap % p.n_tiles;
   const int grid = p.total_tiles < cap ? p.total_tiles : cap;
+  if (grid < p.total_tiles && grid % p.n_tiles != 0) return CTU_E_UNSUPPORTED;   // persistent CTAs must keep their N tile
   const cudaError_t le = launch_pdl(umma_gemm_kernel<BN, STAGES, OUT_BUFS, CTAS_PER_SM, EPI_WARPS>, dim3(grid), dim3(64 + 32 * EPI_WARPS), smem, stream, tmA, tmB, tmC, p);
   count_launch();
   return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
@@ -658,6 +754,7 @@ extern "C" int ctu_umma_gemm(const ctu_gemm_desc* d, void* stream_) {
   p.u3 = d->convt_cout > 0 ? d->u3 : 1;
   p.stats_ld = d->stats_ld; p.out_col0 = d->out_col0;
   p.tma_store = tma_store ? 1 : 0;
+  p.fast = (tma_store && (d->res_mode == CTU_RES_NONE || d->res_mode == CTU_RES_BF16) && d->act == CTU_ACT_NONE) ? 1 : 0;
   const long long tiles_ll = (long long)p.T1 * p.T2 * p.T3 * d->d4 * p.n_tiles;
   if (tiles_ll <= 0 || tiles_ll > 0x7fffffffLL) return CTU_E_BADARG;
   p.total_tiles = (int)tiles_ll;
