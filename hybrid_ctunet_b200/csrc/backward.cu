@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(256) gelu_kernel(const __nv_bfloat16* __restri
     float f[8];
     ld8(x + i * 8, f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752440f));
+    for (int j = 0; j < 8; j += 2) gelu_pair<false>(f[j], f[j + 1], f[j], f[j + 1]);   // packed fp32, one MUFU per element
     st8(y + i * 8, f);
   }
 }

@@ -161,6 +161,66 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+// ---------------------------------------------------------------- packed fp32 (FFMA2 / FMUL2 on sm_100)
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Exact-form GELU 0.5 x (1 + erf(x / sqrt 2)) = x * Phi(x) for TWO values at once, without a reciprocal:
+//   Phi(-|x|) = 0.5 erfc(|x| / sqrt 2) = exp(-x^2 / 2) * P(w),   w = |x| * sqrt(log2(e) / 2)   (so exp(-x^2/2) = 2^(-w^2)),
+// P = degree-10 Chebyshev interpolant of 0.5 erfcx on w in [0, 4.9] (|x| <= 5.77; beyond, 2^(-w^2) < 1e-7 and P is clamped).
+// |gelu - exact| <= 3.1e-6, |Phi - exact| <= 6.8e-6 over [-8, 8] (fp32 Horner; far below the bf16 rounding of the stored
+// result).  One MUFU (ex2) and ~6 issue slots of packed fp32 arithmetic per element; `grad` also returns
+// d/dx = Phi(x) + x phi(x) with the same exponential (phi(x) = 0.3989423 * 2^(-w^2)).
+template <bool GRAD>
+__device__ __forceinline__ void gelu_pair(float xa, float xb, float& ya, float& yb) {
+  constexpr float K = 0.8493218002880191f, WMAX = 4.9f;
+  const float wa = fabsf(xa) * K, wb = fabsf(xb) * K;
+  const uint64_t w = f2_pack(fminf(wa, WMAX), fminf(wb, WMAX));
+  const float ea = ex2_approx(-wa * wa), eb = ex2_approx(-wb * wb);
+  uint64_t p = f2_pack(8.061951625e-07f, 8.061951625e-07f);
+  p = f2_fma(p, w, f2_pack(-2.335833055e-05f, -2.335833055e-05f));
+  p = f2_fma(p, w, f2_pack(2.997489816e-04f, 2.997489816e-04f));
+  p = f2_fma(p, w, f2_pack(-2.258083635e-03f, -2.258083635e-03f));
+  p = f2_fma(p, w, f2_pack(1.120215335e-02f, 1.120215335e-02f));
+  p = f2_fma(p, w, f2_pack(-3.916574339e-02f, -3.916574339e-02f));
+  p = f2_fma(p, w, f2_pack(1.018373904e-01f, 1.018373904e-01f));
+  p = f2_fma(p, w, f2_pack(-2.071734658e-01f, -2.071734658e-01f));
+  p = f2_fma(p, w, f2_pack(3.437036826e-01f, 3.437036826e-01f));
+  p = f2_fma(p, w, f2_pack(-4.693814702e-01f, -4.693814702e-01f));
+  p = f2_fma(p, w, f2_pack(4.999932302e-01f, 4.999932302e-01f));
+  const uint64_t e = f2_pack(ea, eb);
+  float ha, hb;
+  f2_unpack(f2_mul(p, e), ha, hb);                 // Phi(-|x|)
+  const float pa = xa >= 0.f ? 1.f - ha : ha, pb = xb >= 0.f ? 1.f - hb : hb;
+  if (GRAD) {
+    f2_unpack(f2_fma(f2_mul(f2_pack(xa, xb), f2_pack(0.3989422804014327f, 0.3989422804014327f)), e, f2_pack(pa, pb)), ya, yb);
+  } else {
+    ya = xa * pa;
+    yb = xb * pb;
+  }
+}
+
 // Column sums over the 32 lanes of a warp for 32 per-lane values: after the call, lane L holds the sum of
 // v[L] over all lanes (31 shuffles instead of 160).
 __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {

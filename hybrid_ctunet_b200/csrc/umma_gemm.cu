@@ -48,7 +48,7 @@ struct GemmParams {
   int convt_cout, u1, u2, u3;
   int stats_ld, out_col0;
   int tma_store;
-  int fast;  // bf16 rows through the TMA store, no activation, no or bf16 residual: the epilogue takes the lean chunk
+  int fast;  // bf16 rows through the TMA store (any activation, no fp32 residual): the epilogue takes the lean chunk
 };
 
 struct TileCoord {
@@ -105,34 +105,6 @@ struct TileWalker {
     return c;
   }
 };
-
-// Exact-form GELU 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7, far
-// below the bf16 rounding of the stored result): ~15 instructions instead of erff's ~50, the epilogue of the FFN
-// up-projections is otherwise bound by it.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
-}
-
-// d/dx of the exact-erf GELU: Phi(x) + x phi(x), same erf approximation (one exponential serves both terms)
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float ex = __expf(-z * z);  // exp(-x^2 / 2)
-  const float erf_v = copysignf(1.0f - poly * t * ex, x);
-  return fmaf(x * 0.3989422804014327f, ex, 0.5f * (1.0f + erf_v));
-}
 
 template <int BN, int STAGES, int OUT_BUFS, int CTAS_PER_SM, int EPI_WARPS>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, CTAS_PER_SM) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -347,7 +319,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, CTAS_PER_SM) umma_gemm_ke
         }
         if (p.act == CTU_ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < CH; j += 2) gelu_pair<false>(v[j], v[j + 1], v[j], v[j + 1]);
         }
         const int ocol = p.out_col0 + colbase + c0;  // column inside an output row
         if (p.res_mode == CTU_RES_F32 && valid) {
@@ -379,10 +351,15 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, CTAS_PER_SM) umma_gemm_ke
             if (kFull || gcol + j < p.n_real) {
               const uint4 rv = *reinterpret_cast<const uint4*>(rp + j);
               float2 f;
-              f = unpack_bf16x2(rv.x); v[j] *= gelu_erf_grad(f.x); v[j + 1] *= gelu_erf_grad(f.y);
-              f = unpack_bf16x2(rv.y); v[j + 2] *= gelu_erf_grad(f.x); v[j + 3] *= gelu_erf_grad(f.y);
-              f = unpack_bf16x2(rv.z); v[j + 4] *= gelu_erf_grad(f.x); v[j + 5] *= gelu_erf_grad(f.y);
-              f = unpack_bf16x2(rv.w); v[j + 6] *= gelu_erf_grad(f.x); v[j + 7] *= gelu_erf_grad(f.y);
+              const uint32_t u[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                f = unpack_bf16x2(u[h]);
+                float ga, gb;
+                gelu_pair<true>(f.x, f.y, ga, gb);
+                v[j + 2 * h] *= ga;
+                v[j + 2 * h + 1] *= gb;
+              }
             }
           }
         }
@@ -479,20 +456,40 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, CTAS_PER_SM) umma_gemm_ke
                 raw[j + 3] = __float_as_uint(__uint_as_float(raw[j + 3]) + bv.w);
               }
             }
-            if (p.res_mode == CTU_RES_BF16 && valid) {   // (the input-gradient GEMM adding to a gradient already there)
+            if (p.act == CTU_ACT_GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                float ya, yb;
+                gelu_pair<false>(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), ya, yb);
+                raw[j] = __float_as_uint(ya);
+                raw[j + 1] = __float_as_uint(yb);
+              }
+            }
+            if (p.res_mode != CTU_RES_NONE && valid) {
+              // bf16 rows shaped like the output: a gradient that has already arrived (added), or the pre-activation of
+              // the GELU whose derivative scales this input gradient
               const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
                                                                out_row * p.ldr + p.out_col0 + colbase + c0);
               uint4 rv[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) rv[i] = rp[i];
+              const bool gelu_bwd = p.res_mode == CTU_RES_GELU_BWD;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const uint32_t u[4] = {rv[i].x, rv[i].y, rv[i].z, rv[i].w};
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
                   const float2 f = unpack_bf16x2(u[h]);
-                  raw[8 * i + 2 * h] = __float_as_uint(__uint_as_float(raw[8 * i + 2 * h]) + f.x);
-                  raw[8 * i + 2 * h + 1] = __float_as_uint(__uint_as_float(raw[8 * i + 2 * h + 1]) + f.y);
+                  const int j = 8 * i + 2 * h;
+                  if (gelu_bwd) {
+                    float ga, gb;
+                    gelu_pair<true>(f.x, f.y, ga, gb);
+                    raw[j] = __float_as_uint(__uint_as_float(raw[j]) * ga);
+                    raw[j + 1] = __float_as_uint(__uint_as_float(raw[j + 1]) * gb);
+                  } else {
+                    raw[j] = __float_as_uint(__uint_as_float(raw[j]) + f.x);
+                    raw[j + 1] = __float_as_uint(__uint_as_float(raw[j + 1]) + f.y);
+                  }
                 }
               }
             }
@@ -754,7 +751,7 @@ extern "C" int ctu_umma_gemm(const ctu_gemm_desc* d, void* stream_) {
   p.u3 = d->convt_cout > 0 ? d->u3 : 1;
   p.stats_ld = d->stats_ld; p.out_col0 = d->out_col0;
   p.tma_store = tma_store ? 1 : 0;
-  p.fast = (tma_store && (d->res_mode == CTU_RES_NONE || d->res_mode == CTU_RES_BF16) && d->act == CTU_ACT_NONE) ? 1 : 0;
+  p.fast = (tma_store && d->res_mode != CTU_RES_F32) ? 1 : 0;
   const long long tiles_ll = (long long)p.T1 * p.T2 * p.T3 * d->d4 * p.n_tiles;
   if (tiles_ll <= 0 || tiles_ll > 0x7fffffffLL) return CTU_E_BADARG;
   p.total_tiles = (int)tiles_ll;
