@@ -616,38 +616,55 @@ __global__ void __launch_bounds__(256) subsample_bwd_kernel(const __nv_bfloat16*
 // im2col of a single-channel fp32 volume into channels-last bf16 rows [B][Xo][Yo][Zo][kpad] (tap-major columns,
 // taps..kpad-1 zero): lets the C_in = 1 convolutions (ResNet stem forward, and the weight gradients of the stem and of
 // vit_encoder0) run on the tensor-core kernels.
+// One block = a run of IM_ZT output voxels (32 for wide rows, up to 128 for 64-column rows) along z of one (b, xo, yo): the input patch they read (kx x ky x zp floats)
+// is staged in shared memory with coalesced loads, then consecutive threads write consecutive 16-byte tap groups of a
+// voxel row (coalesced stores); `tapoff` maps a tap to its offset inside the patch (-1: zero padding column).
 __global__ void __launch_bounds__(256) im2col_cin1_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out,
                                                           int B, int X, int Y, int Z, int Xo, int Yo, int Zo, int kx,
                                                           int ky, int kz, int sx, int sy, int sz, int px, int py, int pz,
-                                                          int kpad) {
-  // one thread per (output voxel, group of 8 taps): 8 gathered pixels -> one 16-byte store
-  const int gpv = kpad / 8;
-  const long long total = (long long)B * Xo * Yo * Zo * gpv;
+                                                          int kpad, int IM_ZT) {
+  extern __shared__ float im_smem[];
+  const int zp = (IM_ZT - 1) * sz + kz;          // z extent of the patch
   const int taps = kx * ky * kz;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long v = i / gpv;
-    const int grp = (int)(i - v * gpv);
-    const long long vox = v;
-    const int zo = (int)(v % Zo); v /= Zo;
+  float* patch = im_smem;                        // [kx * ky][zp]
+  int* tapoff = reinterpret_cast<int*>(im_smem + ((kx * ky * zp + 3) & ~3));   // [kpad], 16-byte aligned
+  const int zruns = (Zo + IM_ZT - 1) / IM_ZT;
+  const int gpv = kpad / 8;
+  for (int k = threadIdx.x; k < kpad; k += 256) {
+    const int fz = k % kz, fy = (k / kz) % ky, fx = k / (kz * ky);
+    tapoff[k] = k < taps ? (fx * ky + fy) * zp + fz : -1;
+  }
+  const long long blocks = (long long)B * Xo * Yo * zruns;
+  for (long long blk = blockIdx.x; blk < blocks; blk += gridDim.x) {
+    long long v = blk;
+    const int zr = (int)(v % zruns); v /= zruns;
     const int yo = (int)(v % Yo); v /= Yo;
     const int xo = (int)(v % Xo);
     const int b = (int)(v / Xo);
+    const int zo0 = zr * IM_ZT;
+    const int x0 = xo * sx - px, y0 = yo * sy - py, z0 = zo0 * sz - pz;
     const float* ib = img + (long long)b * X * Y * Z;
-    const int x0 = xo * sx - px, y0 = yo * sy - py, z0 = zo * sz - pz;
-    int k = grp * 8;
-    int fz = k % kz, fy = (k / kz) % ky, fx = k / (kz * ky);
-    float val[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float t = 0.f;
-      if (k + e < taps) {
-        const int x = x0 + fx, y = y0 + fy, z = z0 + fz;
-        if (x >= 0 && x < X && y >= 0 && y < Y && z >= 0 && z < Z) t = __ldg(ib + ((long long)x * Y + y) * Z + z);
-      }
-      val[e] = t;
-      if (++fz == kz) { fz = 0; if (++fy == ky) { fy = 0; ++fx; } }
+    __syncthreads();   // the previous tile's patch has been consumed (and tapoff is written)
+    for (int i = threadIdx.x; i < kx * ky * zp; i += 256) {
+      const int zi = i % zp, line = i / zp;
+      const int fy = line % ky, fx = line / ky;
+      const int x = x0 + fx, y = y0 + fy, z = z0 + zi;
+      patch[i] = (x >= 0 && x < X && y >= 0 && y < Y && z >= 0 && z < Z) ? __ldg(ib + ((long long)x * Y + y) * Z + z) : 0.f;
     }
-    st8(out + vox * kpad + grp * 8, val);
+    __syncthreads();
+    const int nz = Zo - zo0 < IM_ZT ? Zo - zo0 : IM_ZT;
+    const long long vox0 = (((long long)b * Xo + xo) * Yo + yo) * Zo + zo0;
+    for (int i = threadIdx.x; i < nz * gpv; i += 256) {
+      const int zi = i / gpv, grp = i - zi * gpv;
+      const int4 o0 = *reinterpret_cast<const int4*>(tapoff + grp * 8);
+      const int4 o1 = *reinterpret_cast<const int4*>(tapoff + grp * 8 + 4);
+      const int off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+      const int zs = zi * sz;
+      float val[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) val[e] = off[e] >= 0 ? patch[off[e] + zs] : 0.f;
+      st8(out + (vox0 + zi) * kpad + grp * 8, val);
+    }
   }
 }
 
@@ -962,9 +979,14 @@ extern "C" int ctu_im2col_cin1(const float* img, void* out, int B, int X, int Y,
                                int sy, int sz, int px, int py, int pz, int kpad, void* stream) {
   if (!img || !out || kpad % 8 || kpad < kx * ky * kz) return CTU_E_BADARG;
   const int Xo = (X + 2 * px - kx) / sx + 1, Yo = (Y + 2 * py - ky) / sy + 1, Zo = (Z + 2 * pz - kz) / sz + 1;
-  const long long nvox = (long long)B * Xo * Yo * Zo;
-  im2col_cin1_kernel<<<bw_grid(nvox * (kpad / 8), 256), 256, 0, (cudaStream_t)stream>>>(img, (bf16*)out, B, X, Y, Z, Xo, Yo, Zo, kx, ky, kz,
-                                                                         sx, sy, sz, px, py, pz, kpad);
+  const int IM_ZT = kpad <= 64 ? (Zo < 128 ? Zo : 128) : 32;   // enough 16-byte stores per block to amortise the staging
+  const long long blocks = (long long)B * Xo * Yo * ((Zo + IM_ZT - 1) / IM_ZT);
+  const int zp = (IM_ZT - 1) * sz + kz;
+  const size_t smem = ((size_t)((kx * ky * zp + 3) & ~3) + kpad) * 4;
+  if (smem > 48 * 1024) return CTU_E_UNSUPPORTED;
+  const long long cap = (long long)bw_num_sms() * 16;
+  im2col_cin1_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, smem, (cudaStream_t)stream>>>(
+      img, (bf16*)out, B, X, Y, Z, Xo, Yo, Zo, kx, ky, kz, sx, sy, sz, px, py, pz, kpad, IM_ZT);
   count_launch();
   return (int)cudaGetLastError();
 }
