@@ -37,6 +37,8 @@ SIGS = {
     "ctu_unpack_grads": (P, I, L, P),
     "ctu_dice_ce_fwd": (P, P, I, I, L, P, P),
     "ctu_dice_ce_bwd": (P, P, I, I, L, P, P, P, P),
+    "ctu_dice_ce_finalize": (P, P, P, P, P, P),
+    "ctu_gather3d": (P, P, I, I, I, I, I, I, I, P, P, P, P),
     "ctu_attention_delta": (P, L, P, L, P, L, I, I, P),
     "ctu_attention_bwd": (P, I, I, I, P, I, P, P, P, P, I, P, P, I, I, I, I, I, I, I, I, P),
 }

@@ -106,6 +106,58 @@ __global__ void __launch_bounds__(256) dice_ce_bwd_kernel(const float* __restric
   }
 }
 
+// One block: the scalar loss of up to CTU_LOSS_MAX_HEADS Dice-CE heads from their accumulated sums, plus everything the
+// backward kernels need for a unit upstream gradient — replaces ~18 tiny torch kernels per head (slices, divisions, means,
+// stacks) between the reduction pass and the gradient pass.  All arithmetic in double.
+__global__ void __launch_bounds__(256) dice_ce_finalize_kernel(const ctu_loss_heads h, const double* __restrict__ sums,
+                                                               float* __restrict__ loss, float* __restrict__ coef,
+                                                               float* __restrict__ ce_scale) {
+  __shared__ double part[256];
+  double acc = 0.0;
+  for (int hd = 0; hd < h.n_heads; ++hd) {
+    const int B = h.B[hd], C = h.C[hd];
+    const double* sh = sums + h.sums_off[hd];
+    float* ch = coef + h.coef_off[hd];
+    const double wd = h.weight[hd] * h.lambda_dice / (double)(B * C);
+    for (int i = threadIdx.x; i < B * C; i += 256) {
+      const double inter = sh[3 * i], den = sh[3 * i + 1] + sh[3 * i + 2] + h.smooth_dr;
+      const double num = 2.0 * inter + h.smooth_nr;
+      acc += wd * (1.0 - num / den);
+      ch[2 * i] = (float)(wd * (-2.0 / den));
+      ch[2 * i + 1] = (float)(wd * (2.0 * num / (den * den)));
+    }
+    if (threadIdx.x == 0) {
+      const double wce = h.weight[hd] * h.lambda_ce / ((double)B * (double)h.S[hd]);
+      acc += wce * sh[3 * B * C];
+      ce_scale[hd] = (float)wce;
+    }
+  }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o >= 1; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = (float)part[0];
+}
+
+// dst[b][xo][yo][zo] = src[b][ix[xo]][iy[yo]][iz[zo]] (0 where an index is negative): nearest-neighbour down-sampling of the label volume with the index
+// tables scipy.ndimage.zoom(order=0) implies (trainer_CTUNet.py:93-94), one launch instead of one index_select per axis.
+__global__ void __launch_bounds__(256) gather3d_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int X,
+                                                       int Y, int Z, int Xo, int Yo, int Zo, const int* __restrict__ ix,
+                                                       const int* __restrict__ iy, const int* __restrict__ iz) {
+  const long long total = (long long)B * Xo * Yo * Zo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long v = i;
+    const int zo = (int)(v % Zo); v /= Zo;
+    const int yo = (int)(v % Yo); v /= Yo;
+    const int xo = (int)(v % Xo);
+    const int b = (int)(v / Xo);
+    const int sx = ix[xo], sy = iy[yo], sz = iz[zo];      // a negative index = outside the volume (scipy's cval = 0)
+    dst[i] = (sx | sy | sz) < 0 ? 0.f : src[(((long long)b * X + sx) * Y + sy) * Z + sz];
+  }
+}
+
 static int loss_grid_x(long long S, int B) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -147,6 +199,28 @@ extern "C" int ctu_dice_ce_bwd(const float* logits, const float* target, int B, 
     case 4: dice_ce_bwd_kernel<4><<<grid, 256, 0, st>>>(logits, target, S, coef, ce_scale, dlogits); break;
     default: return CTU_E_UNSUPPORTED;
   }
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ctu_dice_ce_finalize(const ctu_loss_heads* heads, const double* sums, float* loss, float* coef,
+                                    float* ce_scale, void* stream) {
+  if (!heads || !sums || !loss || !coef || !ce_scale || heads->n_heads <= 0 || heads->n_heads > CTU_LOSS_MAX_HEADS)
+    return CTU_E_BADARG;
+  dice_ce_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*heads, sums, loss, coef, ce_scale);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ctu_gather3d(const float* src, float* dst, int B, int X, int Y, int Z, int Xo, int Yo, int Zo, const int* ix,
+                            const int* iy, const int* iz, void* stream) {
+  if (!src || !dst || !ix || !iy || !iz || B <= 0 || Xo <= 0 || Yo <= 0 || Zo <= 0) return CTU_E_BADARG;
+  const long long total = (long long)B * Xo * Yo * Zo;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long grid = (total + 255) / 256;
+  if (grid > (long long)sms * 16) grid = (long long)sms * 16;
+  gather3d_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(src, dst, B, X, Y, Z, Xo, Yo, Zo, ix, iy, iz);
   count_launch();
   return (int)cudaGetLastError();
 }

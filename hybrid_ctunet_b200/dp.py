@@ -59,6 +59,11 @@ class GradientAllReduce:
         with_grad = [p for p in self.params if p.grad is not None]
         if not with_grad:
             return 0
+        # the gradients of a graph-replayed step are the same tensors every step: plan the pieces once
+        sig = (tuple(p.grad.data_ptr() for p in with_grad), chunks, id(optimizer))
+        plan = getattr(self, "_plan", None)
+        if plan is not None and plan[0] == sig:
+            return self._run_plan(plan, optimizer)
         by_storage = {}
         for p in with_grad:
             by_storage.setdefault(p.grad.untyped_storage().data_ptr(), []).append(p)
@@ -82,33 +87,36 @@ class GradientAllReduce:
         if cur:
             pieces.append((start, lo + total, cur))
         st = span.untyped_storage()
-        nccl = dist.get_backend(self.group) == "nccl"
-        works, views = [], []
-        for a, b, _ in pieces:
-            view = torch.empty(0, dtype=torch.float32, device=span.device).set_(st, a, (b - a,))
-            views.append(view)
-            works.append(dist.all_reduce(view, op=dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM, group=self.group,
-                                         async_op=True))
+        views = [torch.empty(0, dtype=torch.float32, device=span.device).set_(st, a, (b - a,)) for a, b, _ in pieces]
         main_ids = {id(p) for p in main}
         rest = [p for p in with_grad if id(p) not in main_ids]
-        for i, ((_, _, ps), wk) in enumerate(zip(pieces, works)):
+        plan = (sig, views, [ps for _, _, ps in pieces], rest, sum(p.grad.numel() for p in with_grad))
+        self._plan = plan
+        return self._run_plan(plan, optimizer)
+
+    def _run_plan(self, plan, optimizer) -> int:
+        _, views, piece_params, rest, n = plan
+        nccl = dist.get_backend(self.group) == "nccl"
+        works = [dist.all_reduce(v, op=dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM, group=self.group, async_op=True)
+                 for v in views]
+        for i, (ps, wk) in enumerate(zip(piece_params, works)):
             wk.wait()                                   # the current stream waits for piece i only
             if not nccl:
                 views[i].mul_(1.0 / dist.get_world_size(self.group))
-            optimizer.step(only=ps, key=("dp", i, len(pieces)))
+            optimizer.step(only=ps, key=("dp", i, len(views)))
         if rest:                                        # gradients living outside the flat buffer (relative-position tables)
             m = sum(p.grad.numel() for p in rest)
             if self._flat is None or self._flat.numel() != m or self._flat.device != rest[0].grad.device:
                 self._flat = torch.empty(m, dtype=torch.float32, device=rest[0].grad.device)
-            views, off = [], 0
+            fviews, off = [], 0
             for p in rest:
-                views.append(self._flat[off:off + p.grad.numel()].view(p.grad.shape))
+                fviews.append(self._flat[off:off + p.grad.numel()].view(p.grad.shape))
                 off += p.grad.numel()
-            torch._foreach_copy_(views, [p.grad for p in rest])
+            torch._foreach_copy_(fviews, [p.grad for p in rest])
             self._all_reduce_mean(self._flat)
-            torch._foreach_copy_([p.grad for p in rest], views)
+            torch._foreach_copy_([p.grad for p in rest], fviews)
             optimizer.step(only=rest, key=("dp", "rest"))
-        return sum(p.grad.numel() for p in with_grad)
+        return n
 
     def reduce(self) -> int:
         """Average the existing .grad tensors over the group in place; returns the number of elements exchanged."""

@@ -47,6 +47,21 @@ class WgradDesc(C.Structure):
     ]
 
 
+LOSS_MAX_HEADS = 8
+
+
+class LossHeads(C.Structure):
+    """ctu_loss_heads of include/ctunet_b200.h (field for field)."""
+    _fields_ = [
+        ("n_heads", C.c_int32),
+        ("B", C.c_int32 * LOSS_MAX_HEADS), ("C", C.c_int32 * LOSS_MAX_HEADS),
+        ("S", C.c_int64 * LOSS_MAX_HEADS),
+        ("sums_off", C.c_int64 * LOSS_MAX_HEADS), ("coef_off", C.c_int64 * LOSS_MAX_HEADS),
+        ("weight", C.c_double * LOSS_MAX_HEADS),
+        ("lambda_dice", C.c_double), ("lambda_ce", C.c_double), ("smooth_nr", C.c_double), ("smooth_dr", C.c_double),
+    ]
+
+
 def lib_path() -> str:
     return _build.LIB_PATH
 

@@ -100,12 +100,17 @@ class DiceCELoss(nn.Module):
 
 @lru_cache(maxsize=None)
 def zoom_indices(n_in: int, n_out: int) -> Tuple[int, ...]:
-    """Source index per output index of scipy.ndimage.zoom(order=0, prefilter=False, grid_mode=False):
-    nearest neighbour of out_idx * (n_in - 1) / (n_out - 1)."""
+    """Source index per output index of scipy.ndimage.zoom(order=0, prefilter=False, grid_mode=False, mode='constant'):
+    nearest neighbour of out_idx * ((n_in - 1) / (n_out - 1)), the scale rounded to double FIRST as scipy does.  Where that
+    product lands above n_in - 1 by a rounding error (32 -> 16: 15 * (31/15) = 31.000000000000004) scipy treats the sample
+    as outside the volume and writes cval = 0; such positions are returned as -1 (none occur for the reference's
+    96 -> 48 / 96 -> 24 label volumes)."""
     if n_out == 1:
         return (0,)
     pos = np.arange(n_out, dtype=np.float64) * (float(n_in - 1) / float(n_out - 1))
-    return tuple(int(v) for v in np.floor(pos + 0.5).astype(np.int64))
+    idx = np.floor(pos + 0.5).astype(np.int64)
+    idx[pos > float(n_in - 1)] = -1
+    return tuple(int(v) for v in idx)
 
 
 _ZOOM_DEVICE_CACHE = {}
@@ -127,7 +132,12 @@ def zoom_nearest(target: torch.Tensor, zoom: Sequence[float]) -> torch.Tensor:
         n_in = target.shape[ax]
         n_out = int(round(n_in * z))
         if n_out != n_in:
-            out = out.index_select(ax, _zoom_index_tensor(n_in, n_out, target.device))
+            idx = _zoom_index_tensor(n_in, n_out, target.device)
+            out = out.index_select(ax, idx.clamp(min=0))
+            if min(zoom_indices(n_in, n_out)) < 0:      # scipy's out-of-volume samples (cval = 0)
+                shape = [1] * out.dim()
+                shape[ax] = n_out
+                out = out * (idx >= 0).to(out.dtype).view(shape)
     return out
 
 
@@ -136,8 +146,109 @@ def deep_supervision_targets(target: torch.Tensor):
     return zoom_nearest(target, (1, 1, 0.5, 0.5, 1)), zoom_nearest(target, (1, 1, 0.25, 0.25, 0.5))
 
 
+class _MultiHeadDiceCEFused(torch.autograd.Function):
+    """sum_h weight_h * DiceCE(logits_h, target_h) for the heads of one training step: one reduction pass per head
+    (ctu_dice_ce_fwd), ONE finalize launch for the scalar and every backward coefficient (ctu_dice_ce_finalize), one
+    gradient pass per head (ctu_dice_ce_bwd) — no tiny torch kernels in between (they are the serial section between the
+    forward and the backward of the step)."""
+
+    @staticmethod
+    def forward(ctx, cfg, weights, targets, *logits):
+        from . import lib as _lib
+        lib = _lib.require_device()
+        smooth_nr, smooth_dr, lambda_dice, lambda_ce = cfg
+        dev = logits[0].device
+        stream = torch.cuda.current_stream().cuda_stream
+        heads = _lib.LossHeads()
+        heads.n_heads = len(logits)
+        heads.lambda_dice, heads.lambda_ce, heads.smooth_nr, heads.smooth_dr = lambda_dice, lambda_ce, smooth_nr, smooth_dr
+        lg, tg, so, co = [], [], 0, 0
+        for h, (l, t, w) in enumerate(zip(logits, targets, weights)):
+            l = l.float().contiguous()
+            t = t.float().contiguous()
+            B, C = l.shape[:2]
+            S = l.numel() // (B * C)
+            if t.numel() != B * S:
+                raise ValueError(f"ground truth has different shape ({tuple(t.shape)}) from input ({tuple(l.shape)})")
+            heads.B[h], heads.C[h], heads.S[h], heads.weight[h] = B, C, S, float(w)
+            heads.sums_off[h], heads.coef_off[h] = so, co
+            so += B * C * 3 + 1
+            co += B * C * 2
+            lg.append(l)
+            tg.append(t)
+        sums = torch.zeros(so, dtype=torch.float64, device=dev)
+        coef = torch.empty(co, dtype=torch.float32, device=dev)
+        ce_scale = torch.empty(len(logits), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        for h, (l, t) in enumerate(zip(lg, tg)):
+            _lib.check(lib.ctu_dice_ce_fwd(l.data_ptr(), t.data_ptr(), heads.B[h], heads.C[h], heads.S[h],
+                                           sums.data_ptr() + 8 * heads.sums_off[h], stream), "ctu_dice_ce_fwd")
+        import ctypes as C_
+        _lib.check(lib.ctu_dice_ce_finalize(C_.byref(heads), sums.data_ptr(), loss.data_ptr(), coef.data_ptr(),
+                                            ce_scale.data_ptr(), stream), "ctu_dice_ce_finalize")
+        ctx.save_for_backward(coef, ce_scale, *lg, *tg)
+        ctx.meta = [(heads.B[h], heads.C[h], heads.S[h], heads.coef_off[h]) for h in range(len(logits))]
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import lib as _lib
+        lib = _lib.require_device()
+        saved = ctx.saved_tensors
+        n = len(ctx.meta)
+        coef, ce_scale, lg, tg = saved[0], saved[1], saved[2:2 + n], saved[2 + n:2 + 2 * n]
+        gf = g.float()
+        coef_g, ce_g = coef * gf, ce_scale * gf          # the upstream gradient (1, or GradScaler's scale)
+        stream = torch.cuda.current_stream().cuda_stream
+        outs = []
+        for h, (B, C, S, off) in enumerate(ctx.meta):
+            d = torch.empty_like(lg[h])
+            _lib.check(lib.ctu_dice_ce_bwd(lg[h].data_ptr(), tg[h].data_ptr(), B, C, S, coef_g.data_ptr() + 4 * off,
+                                           ce_g.data_ptr() + 4 * h, d.data_ptr(), stream), "ctu_dice_ce_bwd")
+            outs.append(d)
+        return (None, None, None, *outs)
+
+
+_ZOOM_I32_CACHE = {}
+
+
+def _zoom_index_i32(n_in: int, n_out: int, device) -> torch.Tensor:
+    key = (n_in, n_out, str(device))
+    t = _ZOOM_I32_CACHE.get(key)
+    if t is None:
+        t = torch.as_tensor(zoom_indices(n_in, n_out), dtype=torch.int32, device=device)
+        _ZOOM_I32_CACHE[key] = t
+    return t
+
+
+def _gather_targets(target: torch.Tensor, zoom: Sequence[float]) -> torch.Tensor:
+    """zoom_nearest for a CUDA [B, 1, X, Y, Z] label volume in one launch (ctu_gather3d)."""
+    from . import lib as _lib
+    lib = _lib.require_device()
+    t = target.float().contiguous()
+    B, c, X, Y, Z = t.shape
+    Xo, Yo, Zo = int(round(X * zoom[2])), int(round(Y * zoom[3])), int(round(Z * zoom[4]))
+    out = torch.empty(B, c, Xo, Yo, Zo, dtype=torch.float32, device=t.device)
+    ix, iy, iz = (_zoom_index_i32(a, b, t.device) for a, b in ((X, Xo), (Y, Yo), (Z, Zo)))
+    _lib.check(lib.ctu_gather3d(t.data_ptr(), out.data_ptr(), B * c, X, Y, Z, Xo, Yo, Zo, ix.data_ptr(), iy.data_ptr(),
+                                iz.data_ptr(), torch.cuda.current_stream().cuda_stream), "ctu_gather3d")
+    return out
+
+
 def ctunet_loss(logits, target: torch.Tensor, loss_func) -> torch.Tensor:
-    """trainer_CTUNet.py:92-103: loss1 = l(full) + 0.5*(l(1/2) + 0.5*l(1/4)); loss = loss1 + 0.5*(l(vit) + l(vit_96))."""
+    """trainer_CTUNet.py:92-103: loss1 = l(full) + 0.5*(l(1/2) + 0.5*l(1/4)); loss = loss1 + 0.5*(l(vit) + l(vit_96)).
+    With the reference's DiceCELoss configuration on CUDA tensors the five heads go through ONE fused autograd node
+    (_MultiHeadDiceCEFused) and the label volumes are gathered by ctu_gather3d; anything else takes the composition."""
+    heads = (logits[0][0], logits[0][1], logits[0][2], logits[1][0], logits[1][1])
+    import os
+    fused = (os.environ.get("CTU_FUSED_LOSS", "1") != "0"   # (0: the per-head composition, for A/B comparisons)
+             and isinstance(loss_func, DiceCELoss) and loss_func.squared_pred and target.is_cuda and target.dim() == 5
+             and target.shape[1] == 1 and all(h.is_cuda and h.dim() == 5 and h.shape[1] in _FUSED_CLASSES for h in heads))
+    if fused:
+        t1 = _gather_targets(target, (1, 1, 0.5, 0.5, 1))
+        t2 = _gather_targets(target, (1, 1, 0.25, 0.25, 0.5))
+        cfg = (loss_func.smooth_nr, loss_func.smooth_dr, loss_func.lambda_dice, loss_func.lambda_ce)
+        return _MultiHeadDiceCEFused.apply(cfg, (1.0, 0.5, 0.25, 0.5, 0.5), (target, t1, t2, target, target), *heads)
     t1, t2 = deep_supervision_targets(target)
     loss1 = loss_func(logits[0][0], target) + 0.5 * (loss_func(logits[0][1], t1) + 0.5 * loss_func(logits[0][2], t2))
     loss2 = loss_func(logits[1][0], target) + loss_func(logits[1][1], target)

@@ -289,6 +289,30 @@ long long ctu_pack_item_tasks(int unpack, int kind, int rows, int cols, int a, i
 int ctu_pack_weights(const ctu_pack_item* items_dev, int n_items, long long total_units, void* stream);
 int ctu_unpack_grads(const ctu_pack_item* items_dev, int n_items, long long total_units, void* stream);
 
+/* The scalar of the training loss and the coefficients of its backward pass from the sums ctu_dice_ce_fwd accumulated, for
+ * up to CTU_LOSS_MAX_HEADS heads at once (trainer_CTUNet.py:92-103: loss = sum_h weight_h * DiceCE_h):
+ *   loss      = sum_h weight_h * ( lambda_dice * mean_{b,c}[1 - (2 I + nr) / (P + Y + dr)] + lambda_ce * CE_h / (B S_h) )
+ *   coef[h]   = per (b, c) the two factors ctu_dice_ce_bwd expects, for a unit upstream gradient, weight_h folded in
+ *   ce_scale[h] = weight_h * lambda_ce / (B S_h)
+ * sums_off / coef_off: element offsets of head h inside `sums` (doubles, [B][C][3] + 1 per head) and `coef` (floats). */
+#define CTU_LOSS_MAX_HEADS 8
+typedef struct ctu_loss_heads {
+  int32_t n_heads;
+  int32_t B[CTU_LOSS_MAX_HEADS], C[CTU_LOSS_MAX_HEADS];
+  int64_t S[CTU_LOSS_MAX_HEADS];
+  int64_t sums_off[CTU_LOSS_MAX_HEADS], coef_off[CTU_LOSS_MAX_HEADS];
+  double weight[CTU_LOSS_MAX_HEADS];
+  double lambda_dice, lambda_ce, smooth_nr, smooth_dr;
+} ctu_loss_heads;
+int ctu_dice_ce_finalize(const ctu_loss_heads* heads, const double* sums, float* loss, float* coef, float* ce_scale,
+                         void* stream);
+
+/* dst[b][xo][yo][zo] = src[b][ix[xo]][iy[yo]][iz[zo]] (fp32): the deep-supervision label volumes of trainer_CTUNet.py:93-94
+ * (scipy.ndimage.zoom(order=0) == a gather with fixed index tables), one launch per target.  A negative table entry marks a
+ * sample scipy places outside the volume (mode='constant', cval=0): the output there is 0. */
+int ctu_gather3d(const float* src, float* dst, int B, int X, int Y, int Z, int Xo, int Yo, int Zo, const int* ix,
+                 const int* iy, const int* iz, void* stream);
+
 /* Multi-tensor AdamW: the optimizer step of main_CTUNet.py:190-193 (torch.optim.AdamW(lr, weight_decay), no amsgrad) as
  * ONE launch over a device-resident item table — one item per parameter that has a gradient; all four tensors fp32 and
  * contiguous, numel elements each; unit0 = index of the item's first work unit (1024 elements per unit), items sorted by

@@ -78,3 +78,17 @@ def test_no_forbidden_batched_memcpy_symbols():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".sh", ".c", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not any(b in text for b in bad), f
+
+
+def test_loss_heads_struct_matches_header_field_order():
+    from hybrid_ctunet_b200.lib import LOSS_MAX_HEADS, LossHeads
+    src = open(os.path.join(ROOT, "include", "ctunet_b200.h")).read()
+    assert f"#define CTU_LOSS_MAX_HEADS {LOSS_MAX_HEADS}" in src
+    start = src.index("typedef struct ctu_loss_heads {") + len("typedef struct ctu_loss_heads {")
+    body = re.sub(r"/\*.*?\*/", "", src[start:src.index("} ctu_loss_heads;")], flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        m = re.match(r"(int32_t|int64_t|double)\s+(.*)", decl.strip())
+        if m:
+            fields += [re.sub(r"\[.*\]", "", f.strip()) for f in m.group(2).split(",") if f.strip()]
+    assert fields == [f[0] for f in LossHeads._fields_]

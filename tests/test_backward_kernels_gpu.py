@@ -393,3 +393,28 @@ def test_head_backward_fused(C, shape, ld_extra, acc):
     assert rel(db[:ncls], br.grad) < 1e-5
     if ld_extra:   # columns outside the head's slice are untouched
         assert torch.equal(da_full[..., C:], prev[..., C:]) if acc else torch.isnan(da_full[..., C:].float()).all()
+
+
+def test_fused_five_head_loss_equals_the_composition():
+    """losses.ctunet_loss on CUDA (one fused autograd node: 5 reduction passes, ctu_dice_ce_finalize, 5 gradient passes,
+    labels gathered by ctu_gather3d) == the reference's composition of five DiceCELoss terms with scipy-zoomed labels
+    (trainer_CTUNet.py:92-103), value and gradients."""
+    import scipy.ndimage as ndimage
+    from hybrid_ctunet_b200.losses import DiceCELoss, ctunet_loss
+    torch.manual_seed(8)
+    B = 2
+    shapes = [(B, 14, 32, 32, 16), (B, 14, 16, 16, 16), (B, 14, 8, 8, 8), (B, 14, 32, 32, 16), (B, 14, 32, 32, 16)]
+    logits = [torch.randn(*s, device="cuda", requires_grad=True) for s in shapes]
+    target = torch.randint(0, 14, (B, 1, 32, 32, 16), device="cuda").float()
+    lf = DiceCELoss(to_onehot_y=True, softmax=True, squared_pred=True, smooth_nr=0.0, smooth_dr=1e-6)
+    nest = lambda l: ((l[0], l[1], l[2]), (l[3], l[4]))
+    loss = ctunet_loss(nest(logits), target, lf)
+    (loss * 3.0).backward()                     # a non-unit upstream gradient (GradScaler-like)
+    ref_in = [l.detach().clone().requires_grad_() for l in logits]
+    t1 = torch.from_numpy(ndimage.zoom(target.cpu().numpy(), (1, 1, 0.5, 0.5, 1), order=0, prefilter=False)).cuda()
+    t2 = torch.from_numpy(ndimage.zoom(target.cpu().numpy(), (1, 1, 0.25, 0.25, 0.5), order=0, prefilter=False)).cuda()
+    ref = lf(ref_in[0], target) + 0.5 * (lf(ref_in[1], t1) + 0.5 * lf(ref_in[2], t2)) + 0.5 * (lf(ref_in[3], target) + lf(ref_in[4], target))
+    (ref * 3.0).backward()
+    assert abs(float(loss) - float(ref)) < 1e-6 * max(1.0, abs(float(ref)))
+    for a, b in zip(logits, ref_in):
+        assert rel(a.grad, b.grad) < 1e-5

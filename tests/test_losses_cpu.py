@@ -24,6 +24,19 @@ def test_deep_supervision_targets_equal_scipy_zoom():
     assert np.array_equal(t1.numpy(), r1) and np.array_equal(t2.numpy(), r2)
 
 
+def test_zoom_nearest_equals_scipy_on_ragged_sizes_including_out_of_volume_samples():
+    """scipy places out_idx * ((n-1)/(m-1)) a rounding error above n-1 for some sizes (32 -> 16, 48 -> 24) and then writes
+    cval = 0 there; the restatement reproduces it (the reference's 96 -> 48 / 96 -> 24 volumes have no such sample)."""
+    from hybrid_ctunet_b200.losses import zoom_nearest
+    rng = np.random.default_rng(1)
+    assert zoom_indices(32, 16)[-1] == -1 and min(zoom_indices(96, 48)) == 0 and min(zoom_indices(96, 24)) == 0
+    for shape in ((32, 32, 16), (48, 20, 24), (64, 36, 8), (10, 12, 14)):
+        t = rng.integers(1, 14, size=(2, 1) + shape).astype(np.float32)
+        for zoom in ((1, 1, 0.5, 0.5, 1), (1, 1, 0.25, 0.25, 0.5)):
+            ours = zoom_nearest(torch.from_numpy(t), zoom).numpy()
+            assert np.array_equal(ours, ndimage.zoom(t, zoom, order=0, prefilter=False)), (shape, zoom)
+
+
 def test_dice_ce_formula():
     torch.manual_seed(0)
     logits = torch.randn(2, 3, 4, 4, 4, dtype=torch.float64)
