@@ -4,6 +4,7 @@ import ctypes as C
 P, I, L, F, D = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
 
 SIGS = {
+    "ctu_ffn_fused": (P, L, P, P, P, P, P, L, P, L, L, I, I, P),
     "ctu_in_stats": (P, I, I, L, I, P, I, P),
     "ctu_in_apply": (P, I, P, I, P, I, P, I, P, I, I, L, I, F, I, F, P),
     "ctu_layernorm": (P, I, L, P, P, P, L, P, I, L, L, I, F, P),

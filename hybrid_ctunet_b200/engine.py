@@ -24,6 +24,7 @@ import torch
 from . import ops
 from .ops import ACT_GELU, ACT_NONE, OUT_BF16, OUT_F32, OUT_F32_CF, PackedWeight
 
+_FUSED_FFN = os.environ.get("CTU_FUSED_FFN", "1") != "0"   # (0: the two-GEMM inference FFN, for A/B comparisons)
 DS_STRIDE = ((2, 2, 1), (2, 2, 2), (2, 2, 2), (2, 2, 2))
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -1057,6 +1058,12 @@ class Engine:
         n1, n2 = pre + ".net.1", pre + ".net.4"
         hidden = self.w.linear(n1).n_real
         pre_act = None
+        if (self.tape is None and _FUSED_FFN and x.dtype == torch.bfloat16 and out_dtype in (None, torch.bfloat16)
+                and ops.ffn_fused_supported(M, D, hidden)):
+            # inference, 128-channel stage: both GEMMs in one kernel, the [M, hidden] activation never reaches HBM
+            w1, w2 = self.w.get("lin", n1, True), self.w.get("lin", n2, True)
+            if w1.w.shape == (hidden, D) and w2.w.shape == (D, hidden):
+                return ops.ffn_fused(h, w1, w2, x, self._empty(M, D))
         if self.tape is None:
             f = self.gemm(h, "lin", n1, self._empty(M, hidden), dims=(M, 1, 1, 1), extra=True, act=ACT_GELU)
         else:

@@ -134,6 +134,24 @@ def gemm(a: torch.Tensor, w: PackedWeight, out: torch.Tensor, *, dims: Sequence[
     return out
 
 
+def ffn_fused(a: torch.Tensor, w1: PackedWeight, w2: PackedWeight, residual: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out = residual + W2 · GELU(W1 · a + b1) + b2 with the hidden activation kept on chip (ctu_ffn_fused; inference).
+    a / residual / out: bf16 [M, 128] rows; w1: packed [hidden, 128] with bias, w2: packed [128, hidden] with bias."""
+    lib = _lib.require_device()
+    M, Cc = a.shape
+    hidden = w1.n_real
+    assert a.dtype == residual.dtype == out.dtype == torch.bfloat16 and a.stride(-1) == residual.stride(-1) == out.stride(-1) == 1
+    assert w1.w.shape == (hidden, Cc) and w2.w.shape == (Cc, hidden) and w1.bias is not None and w2.bias is not None
+    check(lib.ctu_ffn_fused(a.data_ptr(), int(a.stride(-2)), w1.w.data_ptr(), w1.bias.data_ptr(), w2.w.data_ptr(),
+                            w2.bias.data_ptr(), residual.data_ptr(), int(residual.stride(-2)), out.data_ptr(),
+                            int(out.stride(-2)), M, Cc, hidden, _stream()), "ctu_ffn_fused")
+    return out
+
+
+def ffn_fused_supported(M: int, Cc: int, hidden: int) -> bool:
+    return Cc == 128 and hidden % 128 == 0 and hidden <= 512 and M >= 128
+
+
 # ------------------------------------------------------------------------------------------------ HBM-bound ops
 IN_EPS = 1e-5
 LRELU_SLOPE = 0.01

@@ -75,6 +75,16 @@ typedef struct ctu_gemm_desc {
 
 int ctu_umma_gemm(const ctu_gemm_desc* desc, void* stream);
 
+/* Fused token FeedForward for inference (hybrid_CTUNet.py:513-526 inside Residual :434-440, C = 128 stage):
+ *   out[r,:] = residual[r,:] + W2 · GELU(W1 · a[r,:] + b1) + b2      a = LayerNorm(x) (ctu_layernorm), residual = x
+ * a / residual / out: bf16 rows of C channels (row strides lda / ldr / ldc elements, multiples of 8); w1: bf16 [hidden][C],
+ * w2: bf16 [C][hidden] (nn.Linear layouts, K contiguous); b1 / b2 fp32.  The [M, hidden] activation never leaves the SM
+ * (TMEM accumulator -> GELU -> shared-memory operand of the second tcgen05 GEMM).  C == 128, hidden % 128 == 0 and hidden <= 512, else
+ * CTU_E_UNSUPPORTED (the caller then runs the two-GEMM path). */
+int ctu_ffn_fused(const void* a, long long lda, const void* w1, const float* b1, const void* w2, const float* b2,
+                  const void* residual, long long ldr, void* out, long long ldc, long long M, int C, int hidden,
+                  void* stream);
+
 /* InstanceNorm3d statistics (resnet.py:97,99,101; hybrid_CTUNet.py:85-87): stats[b][c] += (sum, sum of squares)
  * over the S voxels of batch item b.  x: bf16 [B][S][ldx]; stats: fp64 [B][stats_ld][2], zeroed by the caller.
  * The tensor-core kernel accumulates the same format in its epilogue; this standalone pass serves the

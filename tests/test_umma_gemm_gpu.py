@@ -200,3 +200,37 @@ def test_concat_by_offset_and_strided_input():
     ref = a.float() @ w.to(torch.bfloat16).float().t()
     assert _maxrel(out[:, 64:].float(), ref) < 2 ** -7
     assert (out[:, :64] == 0).all()
+
+
+@pytest.mark.parametrize("M,hidden,ld_extra", [(128, 512, 0), (1000, 512, 0), (128 * 148 * 3 + 77, 512, 0), (4096, 256, 64),
+                                               (20000, 384, 0)])
+def test_ffn_fused_matches_the_two_gemm_path_and_fp32(M, hidden, ld_extra):
+    """ctu_ffn_fused (hidden activation on chip: TMEM -> GELU -> shared-memory operand of the second GEMM) against
+    (a) x + W2 gelu(W1 a + b1) + b2 in fp32 with the hidden activation rounded to bf16 where the kernel rounds it, and
+    (b) the two-GEMM path of the same library — hybrid_CTUNet.py:513-526 inside Residual (:434-440).  Ragged last tile,
+    several tiles per CTA (persistent loop), strided rows (views into wider buffers)."""
+    ops = _ops()
+    C = 128
+    g = torch.Generator(device="cuda").manual_seed(M + hidden)
+    w1 = torch.randn(hidden, C, device="cuda", generator=g) / C ** 0.5
+    b1 = torch.randn(hidden, device="cuda", generator=g) * 0.5
+    w2 = torch.randn(C, hidden, device="cuda", generator=g) / hidden ** 0.5
+    b2 = torch.randn(C, device="cuda", generator=g) * 0.5
+    a = torch.randn(M, C + ld_extra, device="cuda", generator=g).to(torch.bfloat16)[:, :C]
+    x = torch.randn(M, C + ld_extra, device="cuda", generator=g).to(torch.bfloat16)[:, :C]
+    p1, p2 = ops.pack_matrix(w1, bias=b1), ops.pack_matrix(w2, bias=b2)
+    out_full = torch.full((M, C + ld_extra), float("nan"), device="cuda", dtype=torch.bfloat16)
+    out = out_full[:, :C]
+    ops.ffn_fused(a, p1, p2, x, out)
+    torch.cuda.synchronize()
+    h = F.gelu(F.linear(a.float(), w1.to(torch.bfloat16).float(), b1)).to(torch.bfloat16).float()
+    ref = x.float() + F.linear(h, w2.to(torch.bfloat16).float(), b2)
+    assert torch.isfinite(out.float()).all()
+    assert _maxrel(out.float(), ref) < 2 ** -7 and _rel(out.float(), ref) < 2 ** -8
+    if ld_extra:
+        assert torch.isnan(out_full[:, C:].float()).all()          # columns outside the view are untouched
+    hid = torch.empty(M, hidden, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a.contiguous(), p1, hid, dims=(M, 1, 1, 1), act=ops.ACT_GELU)
+    two = torch.empty(M, C, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(hid, p2, two, dims=(M, 1, 1, 1), residual=x.contiguous())
+    assert _rel(out.float(), two.float()) < 2 ** -8
