@@ -442,7 +442,7 @@ extern "C" int ctu_ffn_fused(const void* a, long long lda, const void* w1, const
   p.ldr = ldr; p.M = M; p.tiles = (int)tiles; p.nc = hidden / HC;
   static const int dbg = [] { const char* e = getenv("CTU_FFN_DBG"); return e ? atoi(e) : 0; }();
   p.dbg = dbg;
-  static const int epi16 = [] { const char* e = getenv("CTU_FFN_EPI16"); return e ? atoi(e) : 0; }();
+  static const int epi16 = [] { const char* e = getenv("CTU_FFN_EPI16"); return e ? atoi(e) : 1; }();   // measured: 0.39 vs 0.42 ms
   if (epi16) return launch<128, 16>(tmA, tmW1, tmW2, tmOut, p, reinterpret_cast<cudaStream_t>(stream_));
   return launch<128, 8>(tmA, tmW1, tmW2, tmOut, p, reinterpret_cast<cudaStream_t>(stream_));
 }
