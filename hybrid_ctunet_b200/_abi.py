@@ -36,6 +36,7 @@ SIGS = {
     "ctu_adamw_step": (P, I, L, D, D, D, D, D, L, P),
     "ctu_pack_weights": (P, I, L, P),
     "ctu_unpack_grads": (P, I, L, P),
+    "ctu_stats_fold": (P, I, I, I, I, D, P),
     "ctu_dice_ce_fwd": (P, P, I, I, L, P, P),
     "ctu_dice_ce_bwd": (P, P, I, I, L, P, P, P, P),
     "ctu_dice_ce_finalize": (P, P, P, P, P, P),

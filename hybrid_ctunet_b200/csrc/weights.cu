@@ -293,6 +293,41 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const ctu_pack_item* 
         dst[t] = __float2bfloat16((r < it.a && c < it.b) ? src[(long long)r * it.b + c] : 0.f);
         break;
       }
+      // ---- "paired" layouts: two z-neighbouring voxels of a 32-channel tensor share one 64-channel row (slot s = z & 1),
+      // so a 1x1x1 convolution becomes a block-diagonal GEMM and a 3x3x3 convolution a 3x3x3 convolution over pairs whose
+      // z pair-tap pz and slots (s_in, s_out) select the real z tap dz = 2 (pz - 1) + s_in - s_out (zero if |dz| > 1).
+      case CTU_PACK_PAIR_LIN: {  // param [co = a][ci = b]; dst [2 co][2 ci]: (s, o) x (s2, i), zero unless s == s2
+        const int r = (int)(t / it.cols), c = (int)(t % it.cols);
+        const int s = r / it.a, o = r - s * it.a, s2 = c / it.b, i = c - s2 * it.b;
+        dst[t] = __float2bfloat16((s < 2 && s2 < 2 && s == s2) ? src[(long long)o * it.b + i] : 0.f);
+        break;
+      }
+      case CTU_PACK_PAIR_LIN_T: {  // dst [2 ci][2 co]: (s2, i) x (s, o)
+        const int r = (int)(t / it.cols), c = (int)(t % it.cols);
+        const int s2 = r / it.b, i = r - s2 * it.b, s = c / it.a, o = c - s * it.a;
+        dst[t] = __float2bfloat16((s < 2 && s2 < 2 && s == s2) ? src[(long long)o * it.b + i] : 0.f);
+        break;
+      }
+      case CTU_PACK_PAIR_CONV3: {  // param [co = a][ci = b][27]; dst [2 co][27 * 2 ci]: (s, o) x (ptap, s2, i)
+        const int r = (int)(t / it.cols), c = (int)(t % it.cols);
+        const int s = r / it.a, o = r - s * it.a;
+        const int ptap = c / (2 * it.b), rem = c - ptap * 2 * it.b, s2 = rem / it.b, i = rem - s2 * it.b;
+        const int pz = ptap % 3, dz = 2 * (pz - 1) + s2 - s;
+        float v = 0.f;
+        if (s < 2 && ptap < 27 && dz >= -1 && dz <= 1) v = src[((long long)o * it.b + i) * 27 + (ptap - pz) + dz + 1];
+        dst[t] = __float2bfloat16(v);
+        break;
+      }
+      case CTU_PACK_PAIR_CONV3_T: {  // tap-flipped transpose for the input gradient: dst [2 ci][27 * 2 co]: (s2, i) x (26 - ptap, s, o)
+        const int r = (int)(t / it.cols), c = (int)(t % it.cols);
+        const int s2 = r / it.b, i = r - s2 * it.b;
+        const int ft = c / (2 * it.a), rem = c - ft * 2 * it.a, s = rem / it.a, o = rem - s * it.a;
+        const int ptap = 26 - ft, pz = ptap % 3, dz = 2 * (pz - 1) + s2 - s;
+        float v = 0.f;
+        if (s2 < 2 && ft < 27 && dz >= -1 && dz <= 1) v = src[((long long)o * it.b + i) * 27 + (ptap - pz) + dz + 1];
+        dst[t] = __float2bfloat16(v);
+        break;
+      }
       default: break;
     }
   }
@@ -340,8 +375,45 @@ __global__ void __launch_bounds__(256) unpack_grads_kernel(const ctu_pack_item* 
       case CTU_PACK_VEC:
         g[t] = buf[t];
         break;
+      case CTU_PACK_PAIR_LIN: {  // param [co = a][ci = b]; buf [(s, i)][(s, o)]: the two diagonal blocks
+        const int i = (int)(t % it.b), o = (int)(t / it.b);
+        g[t] = buf[(long long)i * ld + o] + buf[(long long)(it.b + i) * ld + it.a + o];
+        break;
+      }
+      case CTU_PACK_PAIR_CONV3: {  // param [co = a][ci = b][27]; buf [(ptap, s2, i)][(s, o)]: every real tap lives in two blocks
+        const int tap = (int)(t % 27), i = (int)((t / 27) % it.b), o = (int)(t / (27LL * it.b));
+        const int dz = tap % 3 - 1, t32 = tap - (tap % 3);   // t32 = (t3 * 3 + t2) * 3
+        float acc = 0.f;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const int num = dz - s2 + s;            // = 2 (pz - 1)
+            if (num == -2 || num == 0 || num == 2) {
+              const int pz = num / 2 + 1;
+              acc += buf[((long long)(t32 + pz) * 2 * it.b + s2 * it.b + i) * ld + s * it.a + o];
+            }
+          }
+        }
+        g[t] = acc;
+        break;
+      }
       default: break;
     }
+  }
+}
+
+// stats [B][ld][width] (fp64): columns c and c + half describe the same channel (paired rows): both become
+// (v[c] + v[c + half]) * scale — scale 0.5 keeps "sum / rows" the channel mean for kernels that divide by the row count.
+__global__ void stats_fold_kernel(double* __restrict__ stats, int B, int ld, int half, int width, double scale) {
+  const int n = B * half * width;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const int w = t % width, c = (t / width) % half, b = t / (width * half);
+    double* lo = stats + ((long long)b * ld + c) * width + w;
+    double* hi = lo + (long long)half * width;
+    const double v = (*lo + *hi) * scale;
+    *lo = v;
+    *hi = v;
   }
 }
 
@@ -368,6 +440,14 @@ extern "C" int ctu_pack_weights(const ctu_pack_item* items_dev, int n_items, lon
 extern "C" int ctu_unpack_grads(const ctu_pack_item* items_dev, int n_items, long long total_units, void* stream) {
   if (!items_dev || n_items <= 0 || total_units <= 0) return CTU_E_BADARG;
   ctu::unpack_grads_kernel<<<ctu::pack_grid(total_units), 256, 0, (cudaStream_t)stream>>>(items_dev, n_items, total_units);
+  ctu::count_launch();
+  return (int)cudaGetLastError();
+}
+
+extern "C" int ctu_stats_fold(double* stats, int B, int ld, int half, int width, double scale, void* stream) {
+  if (!stats || B <= 0 || half <= 0 || width <= 0 || ld < 2 * half) return CTU_E_BADARG;
+  const int n = B * half * width;
+  ctu::stats_fold_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(stats, B, ld, half, width, scale);
   ctu::count_launch();
   return (int)cudaGetLastError();
 }

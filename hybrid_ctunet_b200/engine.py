@@ -56,7 +56,10 @@ def _pad64(v: int) -> int:
 
 
 PACK_LIN, PACK_LIN_T, PACK_CONV3, PACK_CONV3_T, PACK_CONVT, PACK_CONVT_T, PACK_PS, PACK_PS_T, PACK_CIN1, PACK_PS_BIAS, \
-    PACK_VEC = range(11)
+    PACK_VEC, PACK_PAIR_LIN, PACK_PAIR_LIN_T, PACK_PAIR_CONV3, PACK_PAIR_CONV3_T = range(15)
+# ResNet layer 1 (planes = 32, resnet.py:181-186) on "paired" rows: two z-neighbouring voxels per dense 64-channel row
+# instead of 32 live + 32 zero-padded channels per voxel (0: the zero-padded path, for A/B comparisons)
+_PAIR_L1 = os.environ.get("CTU_PAIR_L1", "1") != "0"
 _ITEM_DTYPE = np.dtype([("src", "u8"), ("dst", "u8"), ("kind", "i4"), ("rows", "i4"), ("cols", "i4"), ("a", "i4"),
                         ("b", "i4"), ("c", "i4"), ("unit0", "i8")])
 
@@ -219,6 +222,10 @@ class WeightCache:
             return self.pixel_shuffle(name, extra)
         if kind == "cin1":
             return self.conv_cin1_tc(name)
+        if kind == "pconv1":
+            return self.pair_conv1(name)
+        if kind == "pconv3":
+            return self.pair_conv3(name)
         raise KeyError(kind)
 
     def _p(self, name: str) -> torch.Tensor:
@@ -248,6 +255,17 @@ class WeightCache:
             co, corg = w.shape
             k3 = extra[0] * extra[1] * extra[2]
             return self._packed("psT:" + name, name + ".weight", PACK_PS_T, corg * k3, k3 * co, a=co, b=corg, c=k3)
+        if kind == "pconv1":
+            co, ci = w.shape[:2]
+            pw = self._packed("p1T:" + name, name + ".weight", PACK_PAIR_LIN_T, 2 * ci, 2 * co, a=co, b=ci)
+            pw.alg_flops_per_row = 4.0 * co * ci
+            return pw
+        if kind == "pconv3":
+            co, ci = w.shape[:2]
+            pw = self._packed("p3T:" + name, name + ".weight", PACK_PAIR_CONV3_T, 2 * ci, 27 * 2 * co, a=co, b=ci, ksize=3,
+                              a_c=2 * co)
+            pw.alg_flops_per_row = 4.0 * co * ci * 27
+            return pw
         raise KeyError(kind)
 
     # -- nn.Linear [N, K] (+bias)
@@ -270,6 +288,20 @@ class WeightCache:
         cop, cip = _pad64(co), _pad64(ci)
         pw = self._packed("c3:" + name, name + ".weight", PACK_CONV3, cop, 27 * cip, a=co, b=ci, ksize=3, a_c=cip)
         pw.a_c_live = -(-ci // 16) * 16       # activation rows are zero beyond the layer's true input channels
+        return pw
+
+    # -- the same two layers on paired rows (two z-neighbours per row): block-diagonal [2 Cout, 2 Cin] and the pair-tap
+    #    3x3x3 [2 Cout, 27 * 2 Cin] (CTU_PACK_PAIR_* in include/ctunet_b200.h); FLOPs per (paired) row = two voxels
+    def pair_conv1(self, name: str) -> PackedWeight:
+        co, ci = self._p(name + ".weight").shape[:2]
+        pw = self._packed("p1:" + name, name + ".weight", PACK_PAIR_LIN, 2 * co, 2 * ci, a=co, b=ci)
+        pw.alg_flops_per_row = 4.0 * co * ci
+        return pw
+
+    def pair_conv3(self, name: str) -> PackedWeight:
+        co, ci = self._p(name + ".weight").shape[:2]
+        pw = self._packed("p3:" + name, name + ".weight", PACK_PAIR_CONV3, 2 * co, 27 * 2 * ci, a=co, b=ci, ksize=3, a_c=2 * ci)
+        pw.alg_flops_per_row = 4.0 * co * ci * 27
         return pw
 
     # -- ConvTranspose3d kernel == stride [Cin, Cout, kX, kY, kZ]
@@ -375,6 +407,7 @@ class Tape:
         self.fns: List[Callable[[], None]] = []
         self.grads: Dict[tuple, torch.Tensor] = {}
         self.alias: Dict[tuple, Tuple[torch.Tensor, int]] = {}
+        self.reshaped: Dict[tuple, torch.Tensor] = {}   # key of a reshaped view -> the tensor that owns the gradient
         self.wrecs: List[tuple] = []  # (kind, name, buffer, meta)
 
 
@@ -441,9 +474,19 @@ class Engine:
         if self.tape is not None:
             self.tape.alias[_key(view)] = (base, c0)
 
+    def _reshaped(self, view: torch.Tensor, base: torch.Tensor):
+        """`view` is a contiguous reshape of `base` (same memory, other row width): their gradient is ONE buffer, kept
+        under `base`."""
+        if self.tape is not None:
+            self.tape.reshaped[_key(view)] = base
+
     def _g(self, t: torch.Tensor) -> Optional[torch.Tensor]:
         """Gradient that has arrived for activation `t` (None if no consumer produced one)."""
         k = _key(t)
+        rb = self.tape.reshaped.get(k)
+        if rb is not None:
+            g = self._g(rb)
+            return None if g is None else g.view(t.shape)
         al = self.tape.alias.get(k)
         if al is not None:
             base, c0 = al
@@ -465,6 +508,10 @@ class Engine:
     def _acc(self, t: torch.Tensor, g: torch.Tensor):
         """Add gradient `g` (freshly computed, ownership passes to the tape) to activation `t`."""
         k = _key(t)
+        rb = self.tape.reshaped.get(k)
+        if rb is not None:
+            self._acc(rb, g.view(rb.shape))
+            return
         al = self.tape.alias.get(k)
         if al is not None:
             base, c0 = al
@@ -486,6 +533,8 @@ class Engine:
             ops.accumulate(g, cur)
 
     def _done(self, t: torch.Tensor):
+        if _key(t) in self.tape.reshaped:
+            return
         if _key(t) not in self.tape.alias:
             self.tape.grads.pop(_key(t), None)
 
@@ -640,6 +689,10 @@ class Engine:
                 item = (PACK_PS_BIAS, p.shape[0], 0, buf.numel() // p.shape[0])
             elif kind == "cin1":
                 item = (PACK_CIN1, p.shape[0], p[0].numel(), 0)
+            elif kind == "pconv1":
+                item = (PACK_PAIR_LIN, p.shape[0], p.shape[1], 0)
+            elif kind == "pconv3":
+                item = (PACK_PAIR_CONV3, p.shape[0], p.shape[1], 0)
             else:
                 item = (PACK_VEC, 0, 0, 0)
             recs.append((pname, buf, ld, item))
@@ -753,8 +806,9 @@ class Engine:
         self._rec(bw)
         return out
 
-    def in_apply(self, x, st, *, res=None, rstats=None, out=None):
-        """out = lrelu(IN(x) [+ res | + IN(res)]) (resnet.py:110-124; hybrid_CTUNet.py:95-104)."""
+    def in_apply(self, x, st, *, res=None, rstats=None, out=None, fold: int = 0):
+        """out = lrelu(IN(x) [+ res | + IN(res)]) (resnet.py:110-124; hybrid_CTUNet.py:95-104).  fold: `x` holds paired
+        rows whose column halves [0, fold) and [fold, 2 fold) are the same channels (`st` already folded by the caller)."""
         if out is None:
             out = self._empty(*x.shape)
         ops.in_apply(x, st, out, res=res, rstats=rstats, act=True)
@@ -767,7 +821,7 @@ class Engine:
                 dx = self._empty(*x.shape)
                 dres = self._empty(*res.shape) if res is not None else None
                 ops.in_backward(g, out, x if res is not None else None, st, dx, res=res, rstats=rstats, dres=dres,
-                                sums=self.bsums.take(B, C, 4))
+                                sums=self.bsums.take(B, C, 4), fold=fold)
                 self._acc(x, dx)
                 if res is not None:
                     self._acc(res, dres)
@@ -992,6 +1046,10 @@ class Engine:
         """resnet.py:106-126: 1x1 -> IN -> lrelu -> 3x3x3(stride) -> IN -> lrelu -> 1x1 -> IN (+res) -> lrelu."""
         B = x.shape[0]
         n1, n2, n3 = pre + ".conv1.conv", pre + ".conv2.conv", pre + ".conv3.conv"
+        planes = self.w._p(n1 + ".weight").shape[0]
+        if (_PAIR_L1 and planes == 32 and tuple(stride) == (1, 1, 1) and x.shape[3] % 2 == 0 and x.is_contiguous()
+                and self.w._p(n3 + ".weight").shape[0] % 64 == 0 and x.shape[-1] % 64 == 0):
+            return self._bottleneck_paired(pre, x, has_down)
         st1 = self.stats.take(B, self.w.conv1(n1).n_real)
         a1 = self.in_apply(self.conv1x1(x, n1, st1), st1)
         st2 = self.stats.take(B, self.w.conv3(n2).n_real)
@@ -1017,6 +1075,38 @@ class Engine:
                 self.subsample(x, xs, stride)
             std = self.stats.take(B, self.w.conv1(nd).n_real)
             r = self.conv1x1(xs, nd, std)
+            return self.in_apply(c3, st3, res=r, rstats=std)
+        return self.in_apply(c3, st3, res=x)
+
+    def _bottleneck_paired(self, pre: str, x, has_down: bool):
+        """The same bottleneck for planes = 32 (ResNet layer 1) with the 32-channel tensors held as PAIRED rows: two
+        z-neighbouring voxels per dense 64-channel row ([B, X, Y, Z/2, 64]) instead of 32 live + 32 zero channels per voxel
+        — half the rows through the 3x3x3 convolution, its weight gradient and the InstanceNorm passes, no padding bytes.
+        The 1x1x1 convolutions read / write the un-paired 64- / 128-channel tensors through [.., Z/2, 2 C] views of the
+        same memory with block-diagonal weights; the 3x3x3 convolution runs over pairs (CTU_PACK_PAIR_* layouts).  The
+        InstanceNorm sums of the two column halves are the same channels: ctu_stats_fold merges them."""
+        B, X, Y, Z, Cin = x.shape
+        n1, n2, n3 = pre + ".conv1.conv", pre + ".conv2.conv", pre + ".conv3.conv"
+        cout = self.w._p(n3 + ".weight").shape[0]
+        xp = x.view(B, X, Y, Z // 2, 2 * Cin)
+        self._reshaped(xp, x)
+        st1 = self.stats.take(B, 64)
+        c1 = self.gemm(xp, "pconv1", n1, self._empty(B, X, Y, Z // 2, 64), dims=self._flat_dims(xp), stats=st1)
+        ops.stats_fold(st1, 32, 0.5)
+        a1 = self.in_apply(c1, st1, fold=32)
+        st2 = self.stats.take(B, 64)
+        c2 = self.gemm(a1, "pconv3", n2, self._empty(B, X, Y, Z // 2, 64), dims=self._dims(a1), stats=st2)
+        ops.stats_fold(st2, 32, 0.5)
+        a2 = self.in_apply(c2, st2, fold=32)
+        st3 = self.stats.take(B, 2 * cout)
+        c3p = self.gemm(a2, "pconv1", n3, self._empty(B, X, Y, Z // 2, 2 * cout), dims=self._flat_dims(a2), stats=st3)
+        ops.stats_fold(st3, cout, 1.0)          # consumed as un-paired rows: plain sums over all voxels
+        c3 = c3p.view(B, X, Y, Z, cout)
+        self._reshaped(c3, c3p)
+        if has_down:
+            nd = pre + ".downsample.0.conv"
+            std = self.stats.take(B, self.w.conv1(nd).n_real)
+            r = self.conv1x1(x, nd, std)
             return self.in_apply(c3, st3, res=r, rstats=std)
         return self.in_apply(c3, st3, res=x)
 

@@ -323,7 +323,16 @@ def _bsc(x: torch.Tensor):
     return B, S, C_
 
 
-def in_backward(dout, out, x, xstats, dx, *, res=None, rstats=None, dres=None, sums=None, act: bool = True):
+def stats_fold(stats: torch.Tensor, half: int, scale: float) -> torch.Tensor:
+    """stats: fp64 [B, ld, width] sums of a PAIRED tensor (columns c and c + half are one channel): both halves become
+    (v[c] + v[c + half]) * scale (ctu_stats_fold)."""
+    lib = _lib.require_device()
+    B, ld, width = stats.shape
+    check(lib.ctu_stats_fold(stats.data_ptr(), B, ld, half, width, float(scale), _stream()), "ctu_stats_fold")
+    return stats
+
+
+def in_backward(dout, out, x, xstats, dx, *, res=None, rstats=None, dres=None, sums=None, act: bool = True, fold: int = 0):
     """Backward of in_apply.  dout/out/x(/res): bf16 [B, ..., C]; writes dx (and dres when the forward had a residual:
     the raw gradient g for an identity residual, the InstanceNorm backward for a normalised one).  x may be None when
     the forward had no residual (xhat is recovered from `out`)."""
@@ -339,6 +348,8 @@ def in_backward(dout, out, x, xstats, dx, *, res=None, rstats=None, dres=None, s
                                0 if r2 is None else int(r2.stride(-2)), _ptr(rstats) if res_mode == 2 else None,
                                0 if res_mode != 2 else int(rstats.shape[-2]), B, S, C_, IN_EPS, 1 if act else 0,
                                LRELU_SLOPE, sums.data_ptr(), _stream()), "ctu_in_bwd_stats")
+    if fold:   # paired rows: the two column halves are the same channels
+        stats_fold(sums, fold, 0.5)
     check(lib.ctu_in_bwd_apply(dout.data_ptr(), int(dout.stride(-2)), out.data_ptr(), int(out.stride(-2)), _ptr(x),
                                ldx, xstats.data_ptr(), int(xstats.shape[-2]), _ptr(r2),
                                0 if r2 is None else int(r2.stride(-2)), _ptr(rstats) if res_mode == 2 else None,

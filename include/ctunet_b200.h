@@ -287,6 +287,17 @@ int ctu_ensemble_argmax(const float* p1, const float* p2, int C, long long V, ui
 #define CTU_PACK_CIN1 8
 #define CTU_PACK_PS_BIAS 9
 #define CTU_PACK_VEC 10
+/* "Paired" layouts of the 32-channel ResNet layer-1 bottlenecks (resnet.py:181-186, planes = 32): two z-neighbouring voxels
+ * share one dense 64-channel row (slot s = z & 1) instead of 32 live + 32 zero-padded channels per voxel, so the tensor has
+ * half the rows and no padding.  A 1x1x1 convolution becomes a block-diagonal GEMM, a 3x3x3 convolution a 3x3x3 convolution
+ * over pairs: z pair-tap pz and slots (s_in, s_out) select the real tap dz = 2 (pz - 1) + s_in - s_out (zero if |dz| > 1).
+ *   PAIR_LIN / _T   (a = co, b = ci)  [2 co][2 ci] block diagonal, and its transpose
+ *   PAIR_CONV3 / _T (a = co, b = ci)  [2 co][27 * 2 ci], and the tap-flipped [2 ci][27 * 2 co] of the input gradient
+ * ctu_unpack_grads sums the blocks that hold the same real weight (kinds PAIR_LIN, PAIR_CONV3). */
+#define CTU_PACK_PAIR_LIN 11
+#define CTU_PACK_PAIR_LIN_T 12
+#define CTU_PACK_PAIR_CONV3 13
+#define CTU_PACK_PAIR_CONV3_T 14
 typedef struct ctu_pack_item {
   const void* src;
   void* dst;
@@ -298,6 +309,12 @@ typedef struct ctu_pack_item {
 long long ctu_pack_item_tasks(int unpack, int kind, int rows, int cols, int a, int b, int c);
 int ctu_pack_weights(const ctu_pack_item* items_dev, int n_items, long long total_units, void* stream);
 int ctu_unpack_grads(const ctu_pack_item* items_dev, int n_items, long long total_units, void* stream);
+
+/* InstanceNorm statistics of a PAIRED tensor (see CTU_PACK_PAIR_*): columns c and c + half of stats [B][ld][width] (fp64
+ * sums written by the GEMM epilogue / ctu_in_bwd_stats) belong to the same channel; both become (v[c] + v[c+half]) * scale.
+ * scale = 0.5 for consumers that keep the paired rows (they divide by the paired row count), 1.0 for consumers that read the
+ * tensor as un-paired rows of `half` channels. */
+int ctu_stats_fold(double* stats, int B, int ld, int half, int width, double scale, void* stream);
 
 /* The scalar of the training loss and the coefficients of its backward pass from the sums ctu_dice_ce_fwd accumulated, for
  * up to CTU_LOSS_MAX_HEADS heads at once (trainer_CTUNet.py:92-103: loss = sum_h weight_h * DiceCE_h):
