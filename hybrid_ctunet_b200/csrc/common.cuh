@@ -99,6 +99,66 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The four K16 steps of one 64-wide K block (operands advance 32 bytes = +2 in the descriptors' address field): one asm
+// block, one predicate.  `accumulate` = 0 zero-initialises the accumulator with the FIRST step only.
+__device__ __forceinline__ void umma_bf16_k4(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 a, b;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 q, 0, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "add.u64 a, %1, 2;\n"
+      "add.u64 b, %2, 2;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, q;\n"
+      "add.u64 a, %1, 4;\n"
+      "add.u64 b, %2, 4;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, q;\n"
+      "add.u64 a, %1, 6;\n"
+      "add.u64 b, %2, 6;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %3, q;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Eight instructions whose operand descriptors advance by `step_a` / `step_b` (units of the descriptors' 16-byte address
+// field) — the K loop of the weight-gradient kernels (16 voxels per instruction) as one asm block with one predicate.
+__device__ __forceinline__ void umma_bf16_k8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint64_t step_a,
+                                             uint64_t step_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      ".reg .b64 a, b;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "setp.eq.b32 q, 0, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %5, p;\n"
+      "add.u64 a, %1, %3;\n"
+      "add.u64 b, %2, %4;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, q;\n"
+      "add.u64 a, a, %3;\n"
+      "add.u64 b, b, %4;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, q;\n"
+      "add.u64 a, a, %3;\n"
+      "add.u64 b, b, %4;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, q;\n"
+      "add.u64 a, a, %3;\n"
+      "add.u64 b, b, %4;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, q;\n"
+      "add.u64 a, a, %3;\n"
+      "add.u64 b, b, %4;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, q;\n"
+      "add.u64 a, a, %3;\n"
+      "add.u64 b, b, %4;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, q;\n"
+      "add.u64 a, a, %3;\n"
+      "add.u64 b, b, %4;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, q;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "l"(step_a), "l"(step_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -173,9 +173,13 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_kernel(const __gr
 #pragma unroll
                 for (int h = 0; h < ZT; ++h) {   // the z-adjacent tiles: same weights, views 8 halo rows apart
                   const uint64_t da = halo_desc_a(a_base + (uint32_t)((t2 * HALO_Z + t1 + 8 * h) * 128), p.base_offset_mode, HALO_Z);
+                  if (p.ksteps == 4) {
+                    umma_bf16_k4(acc + (uint32_t)(h * BN), da, db, IDESC, first ? 0u : 1u);
+                  } else {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    if (k < p.ksteps) umma_bf16(acc + (uint32_t)(h * BN), da + 2 * k, db + 2 * k, IDESC, (first && k == 0) ? 0u : 1u);
+                    for (int k = 0; k < 4; ++k) {
+                      if (k < p.ksteps) umma_bf16(acc + (uint32_t)(h * BN), da + 2 * k, db + 2 * k, IDESC, (first && k == 0) ? 0u : 1u);
+                    }
                   }
                 }
                 first = 0;
@@ -325,6 +329,277 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_kernel(const __gr
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// TWO OUTPUT x-PLANES PER TILE for the 64-output-channel layers (conv3_halo_x2_kernel).
+//
+// An M128 x N64 x K16 tcgen05.mma re-reads a 4 KB A tile and a 2 KB B tile from shared memory per 32 tensor-pipe cycles:
+// the N = 64 layers are bound by that operand feed (~2/3 of the N = 128 rate, see conv3_halo_dispatch).  Here a tile is the
+// same 8 (z) x 16 (y) voxels of TWO adjacent planes x, x+1 and the accumulator is 128 columns wide, [plane x | plane x+1].
+// The halo box of input plane p is the A operand of BOTH planes' taps that read it (dx = p - x for plane x, dx - 1 for
+// plane x+1), so for p = x and p = x+1 one N = 128 instruction does the work of two N = 64 ones with ONE read of the A
+// tile (8 KB per 64 cycles: balanced); p = x-1 and p = x+2 feed one plane each (N = 64).  Per (y, z) tap and K16 step:
+// 2 x 64 + 2 x 48 = 224 cycles for two planes instead of 6 x 48 = 288, and four halo boxes instead of six.
+// The weights come from a re-laid copy (CTU_PACK_X3_FROM_PACKED): per (y,z)-tap and N tile the three x-taps are 192
+// consecutive rows [W(dx=+1) | W(0) | W(-1)], so [W(0); W(-1)] (p = x) and [W(+1); W(0)] (p = x+1) are contiguous 128-row
+// operands.  Plane order p = x, x-1, x+1, x+2: the first instruction of a tile (N = 128, no accumulate) initialises both
+// halves of the accumulator.
+template <int SB, int CTAS_PER_SM>
+__global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                         const __grid_constant__ CUtensorMap tmB,
+                                                                         const __grid_constant__ CUtensorMap tmC,
+                                                                         const HaloParams p) {
+  constexpr int BN = 64;
+  constexpr int B_STAGE_BYTES = 128 * 128;        // up to 128 weight rows x 64 K
+  constexpr int TMEM_COLS = 2 * 2 * BN;           // two accumulator slots of [plane x | plane x+1]
+  constexpr uint32_t IDESC64 = umma_idesc_bf16(128, 64);
+  constexpr uint32_t IDESC128 = umma_idesc_bf16(128, 128);
+  constexpr int HALO_Z = halo_z(1);
+  constexpr int HALO_A_BYTES = halo_a_bytes(1);
+  constexpr int HALO_A_STAGE = halo_a_stage(1);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;                                  // one halo stage
+  uint8_t* smem_b = smem_a + HALO_A_STAGE;
+  uint8_t* smem_c = smem_b + SB * B_STAGE_BYTES;           // [2 planes][128 rows x 64 bf16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * HALO_SLAB_BYTES);
+  uint64_t* full_a = bars;
+  uint64_t* empty_a = bars + 1;
+  uint64_t* full_b = bars + 2;
+  uint64_t* empty_b = bars + 2 + SB;
+  uint64_t* bar_tfull = bars + 2 + 2 * SB;
+  uint64_t* bar_tempty = bar_tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  float2* stat_scratch = reinterpret_cast<float2*>(tmem_slot + 2);  // [4][BN]
+
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    mbar_init(smem_u32(&full_a[0]), 1);
+    mbar_init(smem_u32(&empty_a[0]), 1);
+    for (int s = 0; s < SB; ++s) { mbar_init(smem_u32(&full_b[s]), 1); mbar_init(smem_u32(&empty_b[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bar_tfull[s]), 1); mbar_init(smem_u32(&bar_tempty[s]), 4); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  // tile -> (n tile, z tile, y tile, plane pair, batch); p.d3 is the number of plane PAIRS here
+  auto decode = [&](int tile) {
+    HaloTile t;
+    const int n_tile = tile % p.n_tiles;
+    int m = tile / p.n_tiles;
+    t.z0 = (m % p.T1) * 8; m /= p.T1;
+    t.y0 = (m % p.T2) * 16; m /= p.T2;
+    t.x = (m % p.d3) * 2;
+    t.b = m / p.d3;
+    t.n0 = n_tile * BN;
+    return t;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t ia = 0, ib = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const HaloTile t = decode(tile);
+        const int nt = t.n0 / BN;
+#pragma unroll 1
+        for (int pi = 0; pi < 4; ++pi) {
+          const int pl = pi == 0 ? 1 : (pi == 1 ? 0 : pi);        // input plane x - 1 + pl, order 1, 0, 2, 3
+          const int rows = (pl == 1 || pl == 2) ? 128 : 64;
+          const int dxi0 = pl == 0 ? 2 : (pl == 1 ? 1 : 0);       // first x-tap block of the operand: 0: +1, 1: 0, 2: -1
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            {
+              mbar_wait(smem_u32(&empty_a[0]), (ia & 1) ^ 1);
+              const uint32_t full = smem_u32(&full_a[0]);
+              mbar_expect_tx(full, HALO_A_BYTES);
+              tma_load_5d(smem_u32(smem_a), &tmA, full, cb * 64, t.z0 - 1, t.y0 - 1, t.x + pl - 1, t.b);
+              ++ia;
+            }
+            for (int t21 = 0; t21 < 9; ++t21) {
+              const int s = ib % SB;
+              mbar_wait(smem_u32(&empty_b[s]), ((ib / SB) & 1) ^ 1);
+              const uint32_t full = smem_u32(&full_b[s]);
+              mbar_expect_tx(full, rows * 128);
+              const int row0 = ((t21 * p.n_tiles + nt) * 3 + dxi0) * 64;
+              tma_load_2d(smem_u32(smem_b + s * B_STAGE_BYTES), &tmB, full, cb * 64, row0);
+              if (rows == 128) tma_load_2d(smem_u32(smem_b + s * B_STAGE_BYTES + 64 * 128), &tmB, full, cb * 64, row0 + 64);
+              ++ib;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t ia = 0, sbph = 0;
+      int sbi = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        const int slot = lt & 1;
+        mbar_wait(smem_u32(&bar_tempty[slot]), ((lt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(slot * 2 * BN);
+        uint32_t first = 1;
+        // the issuing thread is on the critical path (two CTAs per SM share the tensor pipe): descriptors are a constant
+        // plus a stage / tap offset, the stage index and phase are carried instead of divided out, and the four K16
+        // instructions of a tap are one asm block with a single predicate
+        const uint64_t da0 = halo_desc_a(smem_u32(smem_a), 0, HALO_Z);
+        const uint64_t db0 = umma_desc_k_sw128(smem_u32(smem_b));
+#pragma unroll 1
+        for (int pi = 0; pi < 4; ++pi) {
+          const int pl = pi == 0 ? 1 : (pi == 1 ? 0 : pi);
+          const uint32_t idesc = (pl == 1 || pl == 2) ? IDESC128 : IDESC64;
+          const uint32_t dst = acc + (pl == 3 ? (uint32_t)BN : 0u);
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            mbar_wait(smem_u32(&full_a[0]), ia & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int t21 = 0; t21 < 9; ++t21) {
+              mbar_wait(smem_u32(&full_b[sbi]), sbph);
+              tc_fence_after();
+              const uint64_t db = db0 + (uint64_t)(sbi * (B_STAGE_BYTES >> 4));
+              const uint64_t da = da0 + (uint64_t)((((t21 / 3) * HALO_Z + (t21 % 3)) * 128) >> 4);
+              umma_bf16_k4(dst, da, db, idesc, first ? 0u : 1u);
+              first = 0;
+              umma_commit(smem_u32(&empty_b[sbi]));
+              if (++sbi == SB) { sbi = 0; sbph ^= 1u; }
+            }
+            umma_commit(smem_u32(&empty_a[0]));
+            ++ia;
+          }
+        }
+        umma_commit(smem_u32(&bar_tfull[slot]));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int e = threadIdx.x - 64;
+    const int i1 = r & 7, i2 = r >> 3;
+    float acc_s = 0.f, acc_q = 0.f;   // BN = 64 <= 128 epilogue threads: one statistics column per thread
+    int stat_batch = -1;
+    const int n0_cta = (blockIdx.x % p.n_tiles) * BN;
+    auto flush_stats = [&](int b) {
+      if (b < 0) return;
+      if (e < BN && n0_cta + e < p.n_real) {
+        double* dstp = p.stats + ((long long)b * p.stats_ld + n0_cta + e) * 2;
+        atomicAdd(dstp, (double)acc_s);
+        atomicAdd(dstp + 1, (double)acc_q);
+      }
+      acc_s = acc_q = 0.f;
+    };
+
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const int slot = lt & 1;
+      const HaloTile t = decode(tile);
+      mbar_wait(smem_u32(&bar_tfull[slot]), (lt >> 1) & 1);
+      tc_fence_after();
+      const bool valid = (t.z0 + i1 < p.d1) && (t.y0 + i2 < p.d2);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {   // plane x + h: columns [h * 64, h * 64 + 64) of the accumulator slot
+        uint8_t* cbuf = smem_c + (size_t)h * HALO_SLAB_BYTES;
+        if (e == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // this buffer's previous store has read it
+        named_bar_sync(1, 128);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 2 * BN + h * BN + c0), raw);
+          tmem_ld_wait();
+          if (p.residual != nullptr && valid) {
+            const long long row = (((long long)t.b * (2 * p.d3) + (t.x + h)) * p.d2 + (t.y0 + i2)) * p.d1 + (t.z0 + i1);
+            const __nv_bfloat16* rp = p.residual + row * p.ldr + p.res_col0 + t.n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(rp + j);
+              float2 f;
+              f = unpack_bf16x2(rv.x); raw[j] = __float_as_uint(__uint_as_float(raw[j]) + f.x); raw[j + 1] = __float_as_uint(__uint_as_float(raw[j + 1]) + f.y);
+              f = unpack_bf16x2(rv.y); raw[j + 2] = __float_as_uint(__uint_as_float(raw[j + 2]) + f.x); raw[j + 3] = __float_as_uint(__uint_as_float(raw[j + 3]) + f.y);
+              f = unpack_bf16x2(rv.z); raw[j + 4] = __float_as_uint(__uint_as_float(raw[j + 4]) + f.x); raw[j + 5] = __float_as_uint(__uint_as_float(raw[j + 5]) + f.y);
+              f = unpack_bf16x2(rv.w); raw[j + 6] = __float_as_uint(__uint_as_float(raw[j + 6]) + f.x); raw[j + 7] = __float_as_uint(__uint_as_float(raw[j + 7]) + f.y);
+            }
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
+          const uint32_t base = smem_u32(cbuf) + (uint32_t)(r * 128);
+          const int cbk = (c0 & 63) >> 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t addr = base + (uint32_t)(((cbk + i) ^ (r & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
+                         "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                         : "memory");
+          }
+          if (p.stats != nullptr) {
+            float v[32], sq[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 f = unpack_bf16x2(pk[j]);
+              v[2 * j] = valid ? f.x : 0.f;
+              v[2 * j + 1] = valid ? f.y : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+            const float s_sum = warp_transpose_reduce(v, lane);
+            const float s_sq = warp_transpose_reduce(sq, lane);
+            stat_scratch[q * BN + c0 + lane] = make_float2(s_sum, s_sq);
+          }
+        }
+        if (h == 1) {   // both planes of the accumulator slot have been read
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[slot]));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        named_bar_sync(2, 128);
+        if (e == 0) {
+          if (t.n0 < p.n_real) {
+            asm volatile(
+                "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(&tmC),
+                "r"(smem_u32(cbuf)), "r"(t.n0), "r"(t.z0), "r"(t.y0), "r"(t.x + h), "r"(t.b)
+                : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (p.stats != nullptr) {
+          if (t.b != stat_batch) {
+            flush_stats(stat_batch);
+            stat_batch = t.b;
+          }
+          if (e < BN) {
+            const float2 s0 = stat_scratch[e], s1 = stat_scratch[BN + e], s2 = stat_scratch[2 * BN + e], s3 = stat_scratch[3 * BN + e];
+            acc_s += (s0.x + s1.x) + (s2.x + s3.x);
+            acc_q += (s0.y + s1.y) + (s2.y + s3.y);
+          }
+        }
+      }
+    }
+    if (p.stats != nullptr) flush_stats(stat_batch);
+    if (e == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 static int halo_sm_count() {
   static int n = [] {
     int dev = 0, v = 148;
@@ -356,6 +631,26 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
 
+template <int SB, int CTAS_PER_SM>
+static int launch_halo_x2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const HaloParams& p,
+                          cudaStream_t stream) {
+  constexpr int smem = 1024 + halo_a_stage(1) + SB * 128 * 128 + 2 * HALO_SLAB_BYTES + (2 + 2 * SB + 4) * 8 + 16 + 4 * 64 * 8;
+  static_assert(CTAS_PER_SM * (smem + 1024) <= 228 * 1024, "shared memory budget");
+  static_assert(CTAS_PER_SM * 256 <= 512, "TMEM budget");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3_halo_x2_kernel<SB, CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  int cap = persistent_sms(halo_sm_count()) * CTAS_PER_SM;
+  if (cap > p.n_tiles) cap -= cap % p.n_tiles;
+  const int grid = p.total_tiles < cap ? p.total_tiles : cap;
+  const cudaError_t le = launch_pdl(conv3_halo_x2_kernel<SB, CTAS_PER_SM>, dim3(grid), dim3(192), smem, stream, tmA, tmB, tmC, p);
+  count_launch();
+  return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
+}
+
 // Returns CTU_E_UNSUPPORTED when the problem does not fit this kernel (the caller then uses umma_gemm_kernel).
 int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
   // CTU_CONV_HALO=0 switches this kernel off (A/B comparisons).  Measured on B200, batch 2 (profiles/r01_halo_sweep.txt):
@@ -379,6 +674,10 @@ int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
   // tile + 2 KB B tile: 6 KB per 32 tensor-pipe cycles > 128 B/clk), a ceiling of ~2/3 of the N >= 128 rate.  Off by
   // default.
   const int zt = (d->block_n == 64 && d->d1 % 16 == 0 && variant == 3) ? 2 : 1;
+  // two output x-planes per tile (N = 128 instructions for the two shared input planes): needs the re-laid weight copy
+  static const int x2_mode = [] { const char* e = getenv("CTU_CONV_HALO_X2"); return e ? atoi(e) : 1; }();
+  const bool x2 = x2_mode != 0 && d->block_n == 64 && d->w_x3 != nullptr && d->d3 % 2 == 0 && zt == 1 &&
+                  !(d->a_c == 64 && d->a_c_live > 0 && d->a_c_live < 64);
   CUtensorMap tmA, tmB, tmC;
   {
     cuuint64_t dims[5] = {(cuuint64_t)d->a_c, (cuuint64_t)d->d1, (cuuint64_t)d->d2, (cuuint64_t)d->d3, (cuuint64_t)d->d4};
@@ -394,7 +693,16 @@ int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return CTU_E_DRIVER;
   }
-  {
+  if (x2) {   // w_x3: [9 (y,z) taps][n_pad / 64 N tiles][3 x-taps (+1, 0, -1)][64 rows] x a_c columns
+    cuuint64_t dims[2] = {(cuuint64_t)d->a_c, (cuuint64_t)(9 * (d->n_pad / 64) * 192)};
+    cuuint64_t strides[1] = {(cuuint64_t)d->a_c * 2};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t es[2] = {1, 1};
+    if (tma_encoder()(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w_x3), dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return CTU_E_DRIVER;
+  } else {
     cuuint64_t dims[2] = {(cuuint64_t)d->k_total, (cuuint64_t)d->n_pad};
     cuuint64_t strides[1] = {(cuuint64_t)d->k_total * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)d->block_n};
@@ -435,6 +743,14 @@ int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
   p.total_tiles = (int)tiles;
   // several small CTAs per SM (one halo stage each) beat fewer CTAs with deeper rings: 3 x <64,1,4> reaches 1008
   // TFLOP/s where 2 x <64,2,5> reaches 895 and 1 x <64,3,8> 483
+  if (x2) {
+    p.d3 = d->d3 / 2;                                   // plane pairs
+    p.total_tiles = (int)(tiles / 2);
+    static const int x2_variant = [] { const char* e = getenv("CTU_CONV_HALO_X2_VARIANT"); return e ? atoi(e) : 0; }();
+    if (x2_variant == 1) return launch_halo_x2<4, 1>(tmA, tmB, tmC, p, stream);
+    if (x2_variant == 2) return launch_halo_x2<2, 2>(tmA, tmB, tmC, p, stream);
+    return launch_halo_x2<3, 2>(tmA, tmB, tmC, p, stream);
+  }
   if (d->block_n == 64) {
     if (zt == 2) return launch_halo<64, 1, 4, 2, 2>(tmA, tmB, tmC, p, stream);
     if (variant == 2) return launch_halo<64, 2, 5, 2>(tmA, tmB, tmC, p, stream);

@@ -209,11 +209,9 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, CTAS_PER_SM) umma_gemm_ke
           tc_fence_after();
           const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + s * A_STAGE_BYTES));
           const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + s * B_STAGE_BYTES));
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzled row: +2 in the (addr >> 4) field
-            umma_bf16(acc, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
-          }
+          // four K16 steps: +32 bytes inside the 128-byte swizzled row = +2 in the (addr >> 4) field (one asm block, one
+          // predicate: the issuing thread is on the critical path of the K-heavy shapes)
+          umma_bf16_k4(acc, da, db, IDESC, kb != 0 ? 1u : 0u);
           umma_commit(smem_u32(&bar_empty[s]));
         }
         umma_commit(smem_u32(&bar_tfull[slot]));

@@ -192,11 +192,8 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) umma_wgrad_kernel(const __gr
             tc_fence_after();
             const uint64_t da = umma_desc_mn_sw128(smem_u32(smem_a + sa * WG_A_STAGE_BYTES), WG_SLAB_BYTES);
             const uint32_t acc = tmem_base + (uint32_t)(j * BN);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              // 16 voxels = two 8-row swizzle atoms = 2048 bytes: +128 in the (addr >> 4) field
-              umma_bf16(acc, da + 128 * k, db + 128 * k, IDESC, (vt > w.v0 || k > 0) ? 1u : 0u);
-            }
+            // eight K steps of 16 voxels = two 8-row swizzle atoms = 2048 bytes each: +128 in the (addr >> 4) field
+            umma_bf16_k8(acc, da, db, 128ull, 128ull, IDESC, vt > w.v0 ? 1u : 0u);
             umma_commit(smem_u32(&empty_a[sa]));
             ++ia;
           }

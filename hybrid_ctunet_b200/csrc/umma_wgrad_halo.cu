@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) wgrad_halo_kernel(const __gr
       int li = 0;
       const uint32_t a_base = smem_u32(smem_a);
       const uint32_t b_base = smem_u32(smem_b);
+      const uint64_t db0 = wh_desc(b_base, WH_SLAB_BYTES, 1024);
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++li) {
         const WhItem w = wh_decode(p, item);
         mbar_wait(smem_u32(bar_tempty), (li & 1) ^ 1);
@@ -169,13 +170,11 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) wgrad_halo_kernel(const __gr
               lbo = (uint32_t)WH_TILE_PITCH;
             }
             const uint32_t acc = tmem_base + (uint32_t)((mt - w.m0) * BN);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              // 16 voxels = two y-lines: 2 x 1280 B in the halo tile, 2 x 1024 B in the dY tile
-              const uint64_t da = wh_desc(a_base + off0 + (uint32_t)(k * 2 * WH_Z * 128), lbo, WH_Z * 128);
-              const uint64_t db = wh_desc(b_base + (uint32_t)(k * 2048), WH_SLAB_BYTES, 1024);
-              umma_bf16(acc, da, db, IDESC, (vt > w.v0 || k > 0) ? 1u : 0u);
-            }
+            // eight K steps of 16 voxels = two y-lines each: 2 x 1280 B further in the halo tile, 2 x 1024 B in the dY tile
+            // (one asm block: the issuing thread, not the tensor pipe, bounds this loop when its descriptors are rebuilt
+            // and its predicate re-evaluated per instruction)
+            umma_bf16_k8(acc, wh_desc(a_base + off0, lbo, WH_Z * 128), db0, (uint64_t)((2 * WH_Z * 128) >> 4),
+                         (uint64_t)(2048 >> 4), IDESC, vt > w.v0 ? 1u : 0u);
           }
           umma_commit(smem_u32(bar_empty));
         }

@@ -328,6 +328,14 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const ctu_pack_item* 
         dst[t] = __float2bfloat16(v);
         break;
       }
+      case CTU_PACK_X3_FROM_PACKED: {  // src bf16 [a = n_pad][27 * b], b = a_c = cols; dst rows (t21, n tile, dxi, 64)
+        const __nv_bfloat16* sb = reinterpret_cast<const __nv_bfloat16*>(it.src);
+        const int r = (int)(t / it.cols), c = (int)(t % it.cols);
+        const int per_tap = (it.a / 64) * 192;
+        const int t21 = r / per_tap, rem = r - t21 * per_tap, nt = rem / 192, dxi = (rem % 192) / 64, col = rem % 64;
+        dst[t] = sb[(long long)(nt * 64 + col) * 27 * it.b + (long long)((2 - dxi) * 9 + t21) * it.b + c];
+        break;
+      }
       default: break;
     }
   }

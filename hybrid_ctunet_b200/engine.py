@@ -56,10 +56,12 @@ def _pad64(v: int) -> int:
 
 
 PACK_LIN, PACK_LIN_T, PACK_CONV3, PACK_CONV3_T, PACK_CONVT, PACK_CONVT_T, PACK_PS, PACK_PS_T, PACK_CIN1, PACK_PS_BIAS, \
-    PACK_VEC, PACK_PAIR_LIN, PACK_PAIR_LIN_T, PACK_PAIR_CONV3, PACK_PAIR_CONV3_T = range(15)
+    PACK_VEC, PACK_PAIR_LIN, PACK_PAIR_LIN_T, PACK_PAIR_CONV3, PACK_PAIR_CONV3_T, PACK_X3_FROM_PACKED = range(16)
 # ResNet layer 1 (planes = 32, resnet.py:181-186) on "paired" rows: two z-neighbouring voxels per dense 64-channel row
 # instead of 32 live + 32 zero-padded channels per voxel (0: the zero-padded path, for A/B comparisons)
 _PAIR_L1 = os.environ.get("CTU_PAIR_L1", "1") != "0"
+# 64-output-channel 3x3x3 convolutions on the kernel that computes two x-planes per tile (needs a re-laid weight copy)
+_HALO_X2 = os.environ.get("CTU_CONV_HALO_X2", "1") != "0"
 _ITEM_DTYPE = np.dtype([("src", "u8"), ("dst", "u8"), ("kind", "i4"), ("rows", "i4"), ("cols", "i4"), ("a", "i4"),
                         ("b", "i4"), ("c", "i4"), ("unit0", "i8")])
 
@@ -121,6 +123,7 @@ class WeightCache:
         self.params = params
         self._cache: Dict[str, list] = {}      # key -> [tag, value, item index or None, names, bias repeat(, build)]
         self.items: Optional[ItemTable] = None
+        self.items2: Optional[ItemTable] = None   # second pass: re-laid copies of packed weights (CTU_PACK_X3_FROM_PACKED)
         self.storage_epoch = 0                  # bumped whenever a cached buffer's storage is replaced: CUDA graphs
                                                 # captured over the old buffers are stale from then on
 
@@ -171,9 +174,19 @@ class WeightCache:
             # algorithmic work of one GEMM row with the TRUE channel counts (bench.py's per-class roofline)
             pw.alg_flops_per_row = 2.0 * a * b * (27 if kind in (PACK_CONV3, PACK_CONV3_T) else max(c, 1))
             idx = self.items.add(w.data_ptr(), buf.data_ptr(), kind, n_pad, k_pad, a, b, c)
+            if _HALO_X2 and ksize == 3 and bn == 64 and pw.a_c % 64 == 0 and k_pad == 27 * pw.a_c:
+                # 64-output-channel 3x3x3 layers: the copy the two-plane kernel reads (x-taps of a (y,z)-tap adjacent)
+                if self.items2 is None:
+                    self.items2 = ItemTable(w.device)
+                rows3 = 9 * (n_pad // 64) * 192
+                pw.x3 = torch.empty((rows3, pw.a_c), dtype=BF16, device=w.device)
+                pw.x3_item = self.items2.add(buf.data_ptr(), pw.x3.data_ptr(), PACK_X3_FROM_PACKED, rows3, pw.a_c, n_pad,
+                                             pw.a_c, 0)
         if bias_name and bias_repeat != 1:
             pw.bias.copy_(ps[1].detach().to(F32).repeat(bias_repeat))
         self.items.run("ctu_pack_weights", only=idx)
+        if pw.x3 is not None:
+            self.items2.run("ctu_pack_weights", only=pw.x3_item)
         self._cache[key] = [tag, pw, idx, names, bias_repeat]
         return pw
 
@@ -186,6 +199,8 @@ class WeightCache:
                 return
         if self.items is not None:
             self.items.run("ctu_pack_weights")
+        if self.items2 is not None:
+            self.items2.run("ctu_pack_weights")
         for key in list(self._cache):
             ent = self._cache[key]
             if ent[2] is None:
@@ -206,6 +221,7 @@ class WeightCache:
     def clear(self):
         self._cache.clear()
         self.items = None
+        self.items2 = None
         self.storage_epoch += 1
 
     # -- generic access by (kind, name, extra): forward packing and the packing of the dgrad GEMM
@@ -467,6 +483,8 @@ class Engine:
         CUDA graph is being captured)."""
         if self.w.items is not None:
             self.w.items.device_table()
+        if self.w.items2 is not None:
+            self.w.items2.device_table()
         if getattr(self, "_gtable", None) is not None:
             self._gtable.device_table()
 

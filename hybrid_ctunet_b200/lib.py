@@ -33,6 +33,7 @@ class GemmDesc(C.Structure):
         ("res_mode", C.c_int32), ("ldr", C.c_int32),
         ("convt_cout", C.c_int32), ("u1", C.c_int32), ("u2", C.c_int32), ("u3", C.c_int32),
         ("stats_ld", C.c_int32), ("out_col0", C.c_int32), ("a_c_live", C.c_int32),
+        ("w_x3", C.c_void_p),
     ]
 
 

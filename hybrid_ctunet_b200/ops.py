@@ -55,6 +55,8 @@ class PackedWeight:
     bias: Optional[torch.Tensor] = None                 # fp32 [n_real]
     alg_flops_per_row: float = 0.0                      # algorithmic FLOPs per GEMM row (true channel counts, no padding)
     a_c_live: int = 0                                   # 3x3x3 only: input channels that can be non-zero (0 = all a_c)
+    x3: Optional[torch.Tensor] = None                   # 3x3x3, block_n 64: re-laid copy for the two-plane kernel (w_x3)
+    x3_item: int = -1
 
 
 def pick_block_n(n: int) -> int:
@@ -79,7 +81,18 @@ def pack_matrix(w2d: torch.Tensor, *, ksize: int = 1, a_c: Optional[int] = None,
     if a_c is None:
         a_c = k_pad // (ksize ** 3)
     b = None if bias is None else bias.detach().to(torch.float32).contiguous()
-    return PackedWeight(out, n, a_c, ksize, bn, convt, b)
+    pw = PackedWeight(out, n, a_c, ksize, bn, convt, b)
+    if ksize == 3 and bn == 64 and a_c % 64 == 0 and k_pad == 27 * a_c:
+        pw.x3 = x3_layout(out, a_c)
+    return pw
+
+
+def x3_layout(packed: torch.Tensor, a_c: int) -> torch.Tensor:
+    """CTU_PACK_X3_FROM_PACKED with torch ops: [n_pad][27 * a_c] (tap = (t3 * 3 + t2) * 3 + t1 major) ->
+    [(t2, t1)][n tile][x-tap in the order +1, 0, -1][64 rows] x a_c."""
+    n_pad = packed.shape[0]
+    v = packed.view(n_pad // 64, 64, 3, 9, a_c).flip(2).permute(3, 0, 2, 1, 4)
+    return v.contiguous().view(9 * (n_pad // 64) * 192, a_c)
 
 
 def gemm(a: torch.Tensor, w: PackedWeight, out: torch.Tensor, *, dims: Sequence[int], out_mode: int = OUT_BF16,
@@ -130,6 +143,7 @@ def gemm(a: torch.Tensor, w: PackedWeight, out: torch.Tensor, *, dims: Sequence[
     d.stats_ld = 0 if stats is None else int(stats.shape[-2])
     d.out_col0 = out_col0
     d.a_c_live = w.a_c_live if (w.ksize == 3 and 0 < w.a_c_live < ac) else 0
+    d.w_x3 = w.x3.data_ptr() if (w.x3 is not None and ac == w.a_c) else None
     check(lib.ctu_umma_gemm(C.byref(d), _stream()), "ctu_umma_gemm")
     return out
 

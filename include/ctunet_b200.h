@@ -71,6 +71,8 @@ typedef struct ctu_gemm_desc {
   int32_t a_c_live;     /* 0, or a multiple of 16 <= a_c: channels [a_c_live, a_c) of every `a` row are known to be zero
                            (ResNet layer-1 planes = 32 live in 64-channel rows, resnet.py:181-186): the 3x3x3 kernel skips
                            their K steps */
+  const void* w_x3;     /* NULL, or (k = 3, block_n = 64) the CTU_PACK_X3_FROM_PACKED copy of `w`: enables the kernel that
+                           computes two output x-planes per tile with N = 128 instructions (umma_conv3_halo.cu) */
 } ctu_gemm_desc;
 
 int ctu_umma_gemm(const ctu_gemm_desc* desc, void* stream);
@@ -298,6 +300,10 @@ int ctu_ensemble_argmax(const float* p1, const float* p2, int C, long long V, ui
 #define CTU_PACK_PAIR_LIN_T 12
 #define CTU_PACK_PAIR_CONV3 13
 #define CTU_PACK_PAIR_CONV3_T 14
+/* Re-laid copy of an already packed 3x3x3 weight (src = bf16 [n_pad = a][27 * a_c], a_c = b, tap-major K; run in a SECOND
+ * ctu_pack_weights launch after the one that produced src): dst = bf16 [9 (y,z)-taps][a / 64 N tiles][3 x-taps in the order
+ * dx = +1, 0, -1][64 rows] x a_c columns, so that the weights of two adjacent x-taps are 128 consecutive rows. */
+#define CTU_PACK_X3_FROM_PACKED 15
 typedef struct ctu_pack_item {
   const void* src;
   void* dst;

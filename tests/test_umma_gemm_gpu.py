@@ -105,7 +105,11 @@ def _pack_conv3(w):  # [Cout, Cin, kX, kY, kZ] -> [Cout, 27*Cin] (tap-major, cha
 @pytest.mark.parametrize("B,X,Y,Z,Cin,Cout,bn", [(1, 8, 8, 32, 64, 64, 64), (2, 6, 6, 12, 128, 128, 128),
                                                   (1, 12, 12, 24, 64, 128, 64), (1, 24, 24, 48, 128, 64, 64),
                                                   (1, 5, 7, 9, 64, 64, 64), (1, 96, 96, 96, 64, 64, 64),
-                                                  (2, 3, 32, 32, 128, 64, 64), (1, 4, 16, 48, 64, 64, 64)])
+                                                  (2, 3, 32, 32, 128, 64, 64), (1, 4, 16, 48, 64, 64, 64),
+                                                  # two-plane kernel (X even, Y % 16 == 0, Z % 8 == 0, block_n 64): several
+                                                  # K blocks, two N tiles, a single plane pair, batch > 1
+                                                  (2, 6, 16, 8, 128, 64, 64), (1, 2, 32, 16, 64, 128, 64),
+                                                  (3, 4, 16, 16, 192, 64, 64)])
 def test_conv3x3x3(B, X, Y, Z, Cin, Cout, bn):
     ops = _ops()
     g = torch.Generator(device="cuda").manual_seed(X * Y + Cin)
@@ -140,6 +144,7 @@ def test_conv3x3x3_skips_zero_padded_channels():
     for live in (0, 32):
         pw = ops.pack_matrix(_pack_conv3(w), ksize=3, a_c=64, block_n=64)
         pw.a_c_live = live
+        pw.x3 = None      # both runs on the one-plane kernel (the two-plane kernel has no K-skip and another summation order)
         out = torch.full((B, X, Y, Z, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
         stats = torch.zeros(B, 64, 2, device="cuda", dtype=torch.float64)
         ops.gemm(a, pw, out, dims=(Z, Y, X, B), stats=stats)
