@@ -73,12 +73,13 @@ __device__ __forceinline__ WhItem wh_decode(const WhParams& p, int item) {
 // row offset (in 128-byte lines) of (y, z) tap t21 = ty * 3 + tz inside the halo tile
 __device__ __forceinline__ int wh_tap_off(int t21) { return (t21 / 3) * WH_Z + (t21 % 3); }
 
-template <int BN, int J, int CB, int CTAS_PER_SM>
+template <int BN, int J, int CB, int CTAS_PER_SM, int ST>
 __global__ void __launch_bounds__(192, CTAS_PER_SM) wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                       const __grid_constant__ CUtensorMap tmY,
                                                                       const WhParams p) {
   constexpr int A_BYTES = CB * WH_TILE_PITCH;
   constexpr int B_BYTES = (BN / 64) * WH_SLAB_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // ST stages: one (halo tiles + dY tile) set each
   constexpr int TMEM_COLS = (J * BN <= 128) ? 128 : (J * BN <= 256 ? 256 : 512);
   constexpr uint32_t IDESC = wh_idesc(128, BN);
 
@@ -86,12 +87,12 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) wgrad_halo_kernel(const __gr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + B_BYTES);
-  uint64_t* bar_full = bars;       // halo tile(s) + dY tile landed
-  uint64_t* bar_empty = bars + 1;  // MMAs that read them completed
-  uint64_t* bar_tfull = bars + 2;
-  uint64_t* bar_tempty = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST * STAGE_BYTES);
+  uint64_t* bar_full = bars;            // [ST] halo tile(s) + dY tile landed
+  uint64_t* bar_empty = bars + ST;      // [ST] MMAs that read them completed
+  uint64_t* bar_tfull = bars + 2 * ST;
+  uint64_t* bar_tempty = bars + 2 * ST + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 2);
 
   pdl_trigger();
   const int warp = threadIdx.x >> 5;
@@ -100,8 +101,10 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) wgrad_halo_kernel(const __gr
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmY);
-    mbar_init(smem_u32(bar_full), 1);
-    mbar_init(smem_u32(bar_empty), 1);
+    for (int st = 0; st < ST; ++st) {
+      mbar_init(smem_u32(&bar_full[st]), 1);
+      mbar_init(smem_u32(&bar_empty[st]), 1);
+    }
     mbar_init(smem_u32(bar_tfull), 1);
     mbar_init(smem_u32(bar_tempty), 4);
     mbar_fence_init();
@@ -130,15 +133,17 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) wgrad_halo_kernel(const __gr
           const int y0 = (m % p.T2) * 16; m /= p.T2;
           const int x = m % p.d3;
           const int b = m / p.d3;
-          mbar_wait(smem_u32(bar_empty), (it & 1) ^ 1);
-          const uint32_t full = smem_u32(bar_full);
+          const int st = it % ST;
+          mbar_wait(smem_u32(&bar_empty[st]), ((it / ST) & 1) ^ 1);
+          const uint32_t full = smem_u32(&bar_full[st]);
           mbar_expect_tx(full, CB * WH_TILE_BYTES + B_BYTES);
 #pragma unroll
           for (int cb = 0; cb < CB; ++cb)
-            tma_load_5d(smem_u32(smem_a + cb * WH_TILE_PITCH), &tmX, full, cb * 64, z0 - 1, y0 - 1, x + w.t3 - 1, b);
+            tma_load_5d(smem_u32(smem_a + st * STAGE_BYTES + cb * WH_TILE_PITCH), &tmX, full, cb * 64, z0 - 1, y0 - 1,
+                        x + w.t3 - 1, b);
 #pragma unroll
           for (int sl = 0; sl < BN / 64; ++sl)
-            tma_load_5d(smem_u32(smem_b + sl * WH_SLAB_BYTES), &tmY, full, n0 + sl * 64, z0, y0, x, b);
+            tma_load_5d(smem_u32(smem_b + st * STAGE_BYTES + sl * WH_SLAB_BYTES), &tmY, full, n0 + sl * 64, z0, y0, x, b);
         }
       }
     }
@@ -147,16 +152,18 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) wgrad_halo_kernel(const __gr
     if (lane == 0) {
       uint32_t it = 0;
       int li = 0;
-      const uint32_t a_base = smem_u32(smem_a);
-      const uint32_t b_base = smem_u32(smem_b);
-      const uint64_t db0 = wh_desc(b_base, WH_SLAB_BYTES, 1024);
+      const uint32_t a_base0 = smem_u32(smem_a);
+      const uint32_t b_base0 = smem_u32(smem_b);
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++li) {
         const WhItem w = wh_decode(p, item);
         mbar_wait(smem_u32(bar_tempty), (li & 1) ^ 1);
         tc_fence_after();
         for (int vt = w.v0; vt < w.v1; ++vt, ++it) {
-          mbar_wait(smem_u32(bar_full), it & 1);
+          const int st = it % ST;
+          mbar_wait(smem_u32(&bar_full[st]), (it / ST) & 1);
           tc_fence_after();
+          const uint32_t a_base = a_base0 + (uint32_t)(st * STAGE_BYTES);
+          const uint64_t db0 = wh_desc(b_base0 + (uint32_t)(st * STAGE_BYTES), WH_SLAB_BYTES, 1024);
           for (int mt = w.m0; mt < w.m1; ++mt) {
             // row tile -> start offset of its first slab and the byte distance to its second slab
             uint32_t off0, lbo;
@@ -176,7 +183,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) wgrad_halo_kernel(const __gr
             umma_bf16_k8(acc, wh_desc(a_base + off0, lbo, WH_Z * 128), db0, (uint64_t)((2 * WH_Z * 128) >> 4),
                          (uint64_t)(2048 >> 4), IDESC, vt > w.v0 ? 1u : 0u);
           }
-          umma_commit(smem_u32(bar_empty));
+          umma_commit(smem_u32(&bar_empty[st]));
         }
         umma_commit(smem_u32(bar_tfull));
       }
@@ -243,15 +250,15 @@ static int wh_sm_count() {
   return n;
 }
 
-template <int BN, int J, int CB, int CTAS_PER_SM>
+template <int BN, int J, int CB, int CTAS_PER_SM, int ST = 1>
 static int launch_wh(const CUtensorMap& tmX, const CUtensorMap& tmY, WhParams p, int per_slot, cudaStream_t stream) {
-  constexpr int smem = 1024 + CB * WH_TILE_PITCH + (BN / 64) * WH_SLAB_BYTES + 4 * 8 + 16;
+  constexpr int smem = 1024 + ST * (CB * WH_TILE_PITCH + (BN / 64) * WH_SLAB_BYTES) + (2 * ST + 2) * 8 + 16;
   constexpr int tmem = (J * BN <= 128) ? 128 : (J * BN <= 256 ? 256 : 512);
   static_assert(CTAS_PER_SM * (smem + 1024) <= 228 * 1024, "shared memory budget");
   static_assert(CTAS_PER_SM * tmem <= 512, "TMEM budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel<BN, J, CB, CTAS_PER_SM>,
+    cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel<BN, J, CB, CTAS_PER_SM, ST>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
@@ -267,7 +274,7 @@ static int launch_wh(const CUtensorMap& tmX, const CUtensorMap& tmY, WhParams p,
   p.splits = splits;
   p.total_items = base * splits;
   const int grid = p.total_items < slots ? p.total_items : slots;
-  const cudaError_t le = launch_pdl(wgrad_halo_kernel<BN, J, CB, CTAS_PER_SM>, dim3(grid), dim3(192), smem, stream, tmX, tmY, p);
+  const cudaError_t le = launch_pdl(wgrad_halo_kernel<BN, J, CB, CTAS_PER_SM, ST>, dim3(grid), dim3(192), smem, stream, tmX, tmY, p);
   count_launch();
   return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
@@ -317,18 +324,30 @@ int wgrad_halo_dispatch(const ctu_wgrad_desc* d, cudaStream_t stream) {
   static const int variant = [] { const char* e = getenv("CTU_WGRAD_HALO_VARIANT"); return e ? atoi(e) : 0; }();
   static const int ps_env = [] { const char* e = getenv("CTU_WGRAD_HALO_PER_SLOT"); return e ? atoi(e) : 0; }();
   const int ps = ps_env > 0 ? ps_env : ((p.vox_tiles >= 8000 || d->x_c >= 128) ? 8 : 4);
+  // Variants 2 / 3: ALL (or half of) the row tiles of an x-tap in one item — every (halo tile, dY tile) set is then read by
+  // 3 (or 6) items instead of 9-15: the J = 2 shapes move 9-10 TB/s from L2 to shared memory (ncu: 4.1 GB per launch for
+  // 128 -> 128 @48x48x96, 18x the algorithmic bytes), i.e. they sit at the L2 throughput cap with the tensor pipe 43 % busy.
+  // The wide accumulators leave room for one CTA per SM only, so the loads are pipelined inside the CTA (ST stages).
+  const int ps1 = ps_env > 0 ? ps_env : 2;
   if (d->x_c == 64) {
     if (d->block_n == 64) {
       if (variant == 1) return launch_wh<64, 3, 1, 2>(tmX, tmY, p, ps, stream);
+      if (variant == 2) return launch_wh<64, 5, 1, 1, 3>(tmX, tmY, p, ps1, stream);
+      if (variant == 3) return launch_wh<64, 3, 1, 2, 2>(tmX, tmY, p, ps, stream);
       return launch_wh<64, 2, 1, 4>(tmX, tmY, p, ps, stream);
     }
+    if (variant == 2) return launch_wh<128, 3, 1, 1, 3>(tmX, tmY, p, ps1, stream);
     return launch_wh<128, 2, 1, 2>(tmX, tmY, p, ps, stream);
   }
   if (d->block_n == 64) {
     if (variant == 1) return launch_wh<64, 3, 2, 2>(tmX, tmY, p, ps, stream);
+    if (variant == 2) return launch_wh<64, 5, 2, 1, 3>(tmX, tmY, p, ps1, stream);
     return launch_wh<64, 2, 2, 3>(tmX, tmY, p, ps, stream);
   }
-  return launch_wh<128, 2, 2, 2>(tmX, tmY, p, ps, stream);
+  // 128 -> 128: three row tiles per item on one CTA per SM with a two-stage ring (930 -> 1,129 TFLOP/s at 48x48x96 x 2);
+  // variant 4: the former two-CTA J = 2 shape.  (The wide-J shapes LOSE for 64 output channels: 850 -> 534 TFLOP/s.)
+  if (variant == 4) return launch_wh<128, 2, 2, 2>(tmX, tmY, p, ps, stream);
+  return launch_wh<128, 3, 2, 1, 2>(tmX, tmY, p, ps_env > 0 ? ps_env : 6, stream);   // 4: 1,100, 6: 1,129, 8: 1,088, 16: 971 TFLOP/s
 }
 
 }  // namespace ctu
