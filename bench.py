@@ -212,8 +212,7 @@ class KernelClassProbe:
 
     def result(self, steps: int, graph_step_ms: float):
         agg = {}
-        for kind, shape, e0, e1, fl, by in self.rec:
-            ms = e0.elapsed_time(e1)
+        for kind, shape, ms, fl, by in self.rec:      # (ms already resolved from the event pairs)
             if kind in self.CONTRACTIONS:
                 label, bound = self.CONTRACTIONS[kind]
             else:
@@ -524,17 +523,29 @@ def main():
             # per-class roofline: one eager step of the SAME workload with CUDA events around every launch
             static_grads = [p.grad for p in model.parameters()]  # the graph's outputs: put back after the eager steps
             probe = KernelClassProbe(peaks)
-            for it in range(2):
+            passes = []
+            for it in range(3):
                 if it == 1:
                     probe.install()
+                if it >= 1:
                     # park the GPU on a spin kernel (~0.15 s) while the host enqueues the step: the launches then run
                     # back to back and an event pair brackets kernel time only, not the host's launch latency
+                    probe.rec = []
                     torch.cuda._sleep(int(3e8))
                 for p in model.parameters():
                     p.grad = None
                 ctunet_loss(model(x), y, loss_func).backward()
+                if it >= 1:
+                    sync()
+                    passes.append([(k, sh, e0.elapsed_time(e1), fl, by) for k, sh, e0, e1, fl, by in probe.rec])
             sync()
             probe.remove()
+            # two probed passes, per launch the smaller time: a host hiccup (allocator, GC) while the GPU has caught up
+            # with the enqueueing thread would otherwise be booked on whatever launch it delayed
+            if len(passes[0]) == len(passes[1]):
+                probe.rec = [(a[0], a[1], min(a[2], b[2]), a[3], a[4]) for a, b in zip(passes[0], passes[1])]
+            else:
+                probe.rec = passes[1]
             classes, summary = probe.result(1, ms)
             for p, g in zip(model.parameters(), static_grads):
                 p.grad = g
@@ -661,7 +672,7 @@ def main():
             roofline = {"bound": top["bound"], "kernel": top["class"], "achieved": top["achieved"], "peak": top["peak"],
                         "unit": top["unit"], "frac": top["frac"], "traffic": traffic, "traffic_source": tsrc,
                         "share_of_step": top["share_of_step"], "peak_source": peaks["src"] + ", sustained",
-                        "how": "CUDA events around every launch of one eager step of the benchmark workload (same kernels "
+                        "how": "CUDA events around every launch of two eager steps of the benchmark workload, per launch the smaller time (same kernels "
                                "and arguments as the graph replay, serialised on one stream); achieved = algorithmic "
                                "FLOPs (true channel counts) or bytes (each tensor argument once) of the class / its "
                                "summed launch time; shares are of the summed launch time",
