@@ -343,31 +343,36 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_kernel(const __gr
 // consecutive rows [W(dx=+1) | W(0) | W(-1)], so [W(0); W(-1)] (p = x) and [W(+1); W(0)] (p = x+1) are contiguous 128-row
 // operands.  Plane order p = x, x-1, x+1, x+2: the first instruction of a tile (N = 128, no accumulate) initialises both
 // halves of the accumulator.
-template <int SB, int CTAS_PER_SM>
+// ZT = 2: the tile also spans two z-adjacent 8 x 16 voxel blocks (one 18 x 18 halo box per input plane): every weight stage
+// then feeds four accumulators — the two-plane kernel with ZT = 1 moves 3.7 GB from L2 to shared memory per launch of
+// 64 -> 64 @96^3 x 2 (9.6 TB/s, the L2 throughput cap; ncu), 83 % of it weights.
+template <int SB, int CTAS_PER_SM, int ZT, int SA>
 __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                          const __grid_constant__ CUtensorMap tmB,
                                                                          const __grid_constant__ CUtensorMap tmC,
                                                                          const HaloParams p) {
   constexpr int BN = 64;
   constexpr int B_STAGE_BYTES = 128 * 128;        // up to 128 weight rows x 64 K
-  constexpr int TMEM_COLS = 2 * 2 * BN;           // two accumulator slots of [plane x | plane x+1]
+  constexpr int SLOT_COLS = ZT * 2 * BN;          // one accumulator slot: ZT x [plane x | plane x+1]
+  constexpr int TMEM_COLS = 2 * SLOT_COLS;        // two slots
+  constexpr int NSUB = 2 * ZT;                    // (z block, plane) sub-tiles of 128 voxels x 64 channels
   constexpr uint32_t IDESC64 = umma_idesc_bf16(128, 64);
   constexpr uint32_t IDESC128 = umma_idesc_bf16(128, 128);
-  constexpr int HALO_Z = halo_z(1);
-  constexpr int HALO_A_BYTES = halo_a_bytes(1);
-  constexpr int HALO_A_STAGE = halo_a_stage(1);
+  constexpr int HALO_Z = halo_z(ZT);
+  constexpr int HALO_A_BYTES = halo_a_bytes(ZT);
+  constexpr int HALO_A_STAGE = halo_a_stage(ZT);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;                                  // one halo stage
-  uint8_t* smem_b = smem_a + HALO_A_STAGE;
-  uint8_t* smem_c = smem_b + SB * B_STAGE_BYTES;           // [2 planes][128 rows x 64 bf16]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + 2 * HALO_SLAB_BYTES);
+  uint8_t* smem_a = smem;                                  // SA halo stages
+  uint8_t* smem_b = smem_a + SA * HALO_A_STAGE;
+  uint8_t* smem_c = smem_b + SB * B_STAGE_BYTES;           // [NSUB][128 rows x 64 bf16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + NSUB * HALO_SLAB_BYTES);
   uint64_t* full_a = bars;
-  uint64_t* empty_a = bars + 1;
-  uint64_t* full_b = bars + 2;
-  uint64_t* empty_b = bars + 2 + SB;
-  uint64_t* bar_tfull = bars + 2 + 2 * SB;
+  uint64_t* empty_a = bars + SA;
+  uint64_t* full_b = bars + 2 * SA;
+  uint64_t* empty_b = bars + 2 * SA + SB;
+  uint64_t* bar_tfull = bars + 2 * SA + 2 * SB;
   uint64_t* bar_tempty = bar_tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
   float2* stat_scratch = reinterpret_cast<float2*>(tmem_slot + 2);  // [4][BN]
@@ -380,8 +385,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const _
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
-    mbar_init(smem_u32(&full_a[0]), 1);
-    mbar_init(smem_u32(&empty_a[0]), 1);
+    for (int st = 0; st < SA; ++st) { mbar_init(smem_u32(&full_a[st]), 1); mbar_init(smem_u32(&empty_a[st]), 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(smem_u32(&full_b[s]), 1); mbar_init(smem_u32(&empty_b[s]), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bar_tfull[s]), 1); mbar_init(smem_u32(&bar_tempty[s]), 4); }
     mbar_fence_init();
@@ -401,7 +405,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const _
     HaloTile t;
     const int n_tile = tile % p.n_tiles;
     int m = tile / p.n_tiles;
-    t.z0 = (m % p.T1) * 8; m /= p.T1;
+    t.z0 = (m % p.T1) * (8 * ZT); m /= p.T1;
     t.y0 = (m % p.T2) * 16; m /= p.T2;
     t.x = (m % p.d3) * 2;
     t.b = m / p.d3;
@@ -423,10 +427,11 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const _
           const int dxi0 = pl == 0 ? 2 : (pl == 1 ? 1 : 0);       // first x-tap block of the operand: 0: +1, 1: 0, 2: -1
           for (int cb = 0; cb < p.cblocks; ++cb) {
             {
-              mbar_wait(smem_u32(&empty_a[0]), (ia & 1) ^ 1);
-              const uint32_t full = smem_u32(&full_a[0]);
+              const int sa = ia % SA;
+              mbar_wait(smem_u32(&empty_a[sa]), ((ia / SA) & 1) ^ 1);
+              const uint32_t full = smem_u32(&full_a[sa]);
               mbar_expect_tx(full, HALO_A_BYTES);
-              tma_load_5d(smem_u32(smem_a), &tmA, full, cb * 64, t.z0 - 1, t.y0 - 1, t.x + pl - 1, t.b);
+              tma_load_5d(smem_u32(smem_a + sa * HALO_A_STAGE), &tmA, full, cb * 64, t.z0 - 1, t.y0 - 1, t.x + pl - 1, t.b);
               ++ia;
             }
             for (int t21 = 0; t21 < 9; ++t21) {
@@ -453,12 +458,11 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const _
         const int slot = lt & 1;
         mbar_wait(smem_u32(&bar_tempty[slot]), ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t acc = tmem_base + (uint32_t)(slot * 2 * BN);
+        const uint32_t acc = tmem_base + (uint32_t)(slot * SLOT_COLS);
         uint32_t first = 1;
         // the issuing thread is on the critical path (two CTAs per SM share the tensor pipe): descriptors are a constant
         // plus a stage / tap offset, the stage index and phase are carried instead of divided out, and the four K16
         // instructions of a tap are one asm block with a single predicate
-        const uint64_t da0 = halo_desc_a(smem_u32(smem_a), 0, HALO_Z);
         const uint64_t db0 = umma_desc_k_sw128(smem_u32(smem_b));
 #pragma unroll 1
         for (int pi = 0; pi < 4; ++pi) {
@@ -466,20 +470,24 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const _
           const uint32_t idesc = (pl == 1 || pl == 2) ? IDESC128 : IDESC64;
           const uint32_t dst = acc + (pl == 3 ? (uint32_t)BN : 0u);
           for (int cb = 0; cb < p.cblocks; ++cb) {
-            mbar_wait(smem_u32(&full_a[0]), ia & 1);
+            const int sa = ia % SA;
+            mbar_wait(smem_u32(&full_a[sa]), (ia / SA) & 1);
             tc_fence_after();
+            const uint64_t da0 = halo_desc_a(smem_u32(smem_a + sa * HALO_A_STAGE), 0, HALO_Z);
 #pragma unroll
             for (int t21 = 0; t21 < 9; ++t21) {
               mbar_wait(smem_u32(&full_b[sbi]), sbph);
               tc_fence_after();
               const uint64_t db = db0 + (uint64_t)(sbi * (B_STAGE_BYTES >> 4));
               const uint64_t da = da0 + (uint64_t)((((t21 / 3) * HALO_Z + (t21 % 3)) * 128) >> 4);
-              umma_bf16_k4(dst, da, db, idesc, first ? 0u : 1u);
+#pragma unroll
+              for (int h = 0; h < ZT; ++h)   // the z-adjacent blocks: same weights, views 8 halo rows further
+                umma_bf16_k4(dst + (uint32_t)(h * 2 * BN), da + (uint64_t)((8 * h * 128) >> 4), db, idesc, first ? 0u : 1u);
               first = 0;
               umma_commit(smem_u32(&empty_b[sbi]));
               if (++sbi == SB) { sbi = 0; sbph ^= 1u; }
             }
-            umma_commit(smem_u32(&empty_a[0]));
+            umma_commit(smem_u32(&empty_a[sa]));
             ++ia;
           }
         }
@@ -511,19 +519,24 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const _
       const HaloTile t = decode(tile);
       mbar_wait(smem_u32(&bar_tfull[slot]), (lt >> 1) & 1);
       tc_fence_after();
-      const bool valid = (t.z0 + i1 < p.d1) && (t.y0 + i2 < p.d2);
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {   // plane x + h: columns [h * 64, h * 64 + 64) of the accumulator slot
-        uint8_t* cbuf = smem_c + (size_t)h * HALO_SLAB_BYTES;
-        if (e == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // this buffer's previous store has read it
+      for (int sub = 0; sub < NSUB; ++sub) {   // z block zb, plane x + h: columns [sub * 64, sub * 64 + 64) of the slot
+        const int zb = sub >> 1, h = sub & 1;
+        const int zt0 = t.z0 + 8 * zb;
+        const bool valid = (zt0 + i1 < p.d1) && (t.y0 + i2 < p.d2);
+        uint8_t* cbuf = smem_c + (size_t)sub * HALO_SLAB_BYTES;
+        if (e == 0) {   // this buffer's previous store (NSUB groups ago) has read it
+          if (NSUB == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+        }
         named_bar_sync(1, 128);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t raw[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 2 * BN + h * BN + c0), raw);
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * SLOT_COLS + sub * BN + c0), raw);
           tmem_ld_wait();
           if (p.residual != nullptr && valid) {
-            const long long row = (((long long)t.b * (2 * p.d3) + (t.x + h)) * p.d2 + (t.y0 + i2)) * p.d1 + (t.z0 + i1);
+            const long long row = (((long long)t.b * (2 * p.d3) + (t.x + h)) * p.d2 + (t.y0 + i2)) * p.d1 + (zt0 + i1);
             const __nv_bfloat16* rp = p.residual + row * p.ldr + p.res_col0 + t.n0 + c0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
@@ -562,7 +575,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const _
             stat_scratch[q * BN + c0 + lane] = make_float2(s_sum, s_sq);
           }
         }
-        if (h == 1) {   // both planes of the accumulator slot have been read
+        if (sub == NSUB - 1) {   // every sub-tile of the accumulator slot has been read
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[slot]));
@@ -573,7 +586,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const _
           if (t.n0 < p.n_real) {
             asm volatile(
                 "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(&tmC),
-                "r"(smem_u32(cbuf)), "r"(t.n0), "r"(t.z0), "r"(t.y0), "r"(t.x + h), "r"(t.b)
+                "r"(smem_u32(cbuf)), "r"(t.n0), "r"(zt0), "r"(t.y0), "r"(t.x + h), "r"(t.b)
                 : "memory");
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -631,22 +644,23 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
 
-template <int SB, int CTAS_PER_SM>
+template <int SB, int CTAS_PER_SM, int ZT = 1, int SA = 1>
 static int launch_halo_x2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const HaloParams& p,
                           cudaStream_t stream) {
-  constexpr int smem = 1024 + halo_a_stage(1) + SB * 128 * 128 + 2 * HALO_SLAB_BYTES + (2 + 2 * SB + 4) * 8 + 16 + 4 * 64 * 8;
+  constexpr int smem = 1024 + SA * halo_a_stage(ZT) + SB * 128 * 128 + 2 * ZT * HALO_SLAB_BYTES + (2 * SA + 2 * SB + 4) * 8 + 16 +
+                       4 * 64 * 8;
   static_assert(CTAS_PER_SM * (smem + 1024) <= 228 * 1024, "shared memory budget");
-  static_assert(CTAS_PER_SM * 256 <= 512, "TMEM budget");
+  static_assert(CTAS_PER_SM * 4 * ZT * 64 <= 512, "TMEM budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv3_halo_x2_kernel<SB, CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv3_halo_x2_kernel<SB, CTAS_PER_SM, ZT, SA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   int cap = persistent_sms(halo_sm_count()) * CTAS_PER_SM;
   if (cap > p.n_tiles) cap -= cap % p.n_tiles;
   const int grid = p.total_tiles < cap ? p.total_tiles : cap;
-  const cudaError_t le = launch_pdl(conv3_halo_x2_kernel<SB, CTAS_PER_SM>, dim3(grid), dim3(192), smem, stream, tmA, tmB, tmC, p);
+  const cudaError_t le = launch_pdl(conv3_halo_x2_kernel<SB, CTAS_PER_SM, ZT, SA>, dim3(grid), dim3(192), smem, stream, tmA, tmB, tmC, p);
   count_launch();
   return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
@@ -678,6 +692,11 @@ int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
   static const int x2_mode = [] { const char* e = getenv("CTU_CONV_HALO_X2"); return e ? atoi(e) : 1; }();
   const bool x2 = x2_mode != 0 && d->block_n == 64 && d->w_x3 != nullptr && d->d3 % 2 == 0 && zt == 1 &&
                   !(d->a_c == 64 && d->a_c_live > 0 && d->a_c_live < 64);
+  // CTU_CONV_HALO_X2_ZT=2 (opt-in): two z blocks per tile on ONE CTA per SM (TMEM 512 columns): 43 % less L2 -> shared-memory
+  // traffic, but measured SLOWER (64->64 @96^3 x 4: 0.764 vs 0.706 ms; 128->64 1.435 vs 1.324) — one issuing thread and one
+  // epilogue per SM lose more than the traffic saves, as with every one-CTA-per-SM shape tried in this file.
+  static const int x2_zt = [] { const char* e = getenv("CTU_CONV_HALO_X2_ZT"); return e ? atoi(e) : 1; }();
+  const int zt_box = (x2 && x2_zt == 2 && d->d1 % 16 == 0) ? 2 : zt;   // z blocks per tile (halo box 18 instead of 10 deep)
   CUtensorMap tmA, tmB, tmC;
   {
     cuuint64_t dims[5] = {(cuuint64_t)d->a_c, (cuuint64_t)d->d1, (cuuint64_t)d->d2, (cuuint64_t)d->d3, (cuuint64_t)d->d4};
@@ -686,7 +705,7 @@ int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
     strides[1] = strides[0] * d->d1;
     strides[2] = strides[1] * d->d2;
     strides[3] = strides[2] * d->d3;
-    cuuint32_t box[5] = {64, (cuuint32_t)halo_z(zt), HALO_Y, 1, 1};
+    cuuint32_t box[5] = {64, (cuuint32_t)halo_z(zt_box), HALO_Y, 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     if (tma_encoder()(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(d->a), dims, strides, box, es,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
@@ -746,6 +765,11 @@ int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
   if (x2) {
     p.d3 = d->d3 / 2;                                   // plane pairs
     p.total_tiles = (int)(tiles / 2);
+    if (zt_box == 2) {
+      p.T1 = d->d1 / 16;
+      p.total_tiles /= 2;
+      return launch_halo_x2<4, 1, 2, 2>(tmA, tmB, tmC, p, stream);
+    }
     static const int x2_variant = [] { const char* e = getenv("CTU_CONV_HALO_X2_VARIANT"); return e ? atoi(e) : 0; }();
     if (x2_variant == 1) return launch_halo_x2<4, 1>(tmA, tmB, tmC, p, stream);
     if (x2_variant == 2) return launch_halo_x2<2, 2>(tmA, tmB, tmC, p, stream);
