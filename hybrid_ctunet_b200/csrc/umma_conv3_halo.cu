@@ -346,7 +346,9 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_kernel(const __gr
 // ZT = 2: the tile also spans two z-adjacent 8 x 16 voxel blocks (one 18 x 18 halo box per input plane): every weight stage
 // then feeds four accumulators — the two-plane kernel with ZT = 1 moves 3.7 GB from L2 to shared memory per launch of
 // 64 -> 64 @96^3 x 2 (9.6 TB/s, the L2 throughput cap; ncu), 83 % of it weights.
-template <int SB, int CTAS_PER_SM, int ZT, int SA>
+// SLOTS = 1: a single accumulator slot and ONE staging buffer per CTA (72 KB of shared memory, 128 TMEM columns): three
+// CTAs per SM — the epilogue of a CTA then blocks its own main loop, the two other CTAs keep the tensor pipe fed.
+template <int SB, int CTAS_PER_SM, int ZT, int SA, int SLOTS>
 __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                          const __grid_constant__ CUtensorMap tmB,
                                                                          const __grid_constant__ CUtensorMap tmC,
@@ -354,7 +356,8 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const _
   constexpr int BN = 64;
   constexpr int B_STAGE_BYTES = 128 * 128;        // up to 128 weight rows x 64 K
   constexpr int SLOT_COLS = ZT * 2 * BN;          // one accumulator slot: ZT x [plane x | plane x+1]
-  constexpr int TMEM_COLS = 2 * SLOT_COLS;        // two slots
+  constexpr int TMEM_COLS = SLOTS * SLOT_COLS;
+  constexpr int CBUFS = SLOTS == 1 ? 1 : 2 * ZT;  // staging buffers
   constexpr int NSUB = 2 * ZT;                    // (z block, plane) sub-tiles of 128 voxels x 64 channels
   constexpr uint32_t IDESC64 = umma_idesc_bf16(128, 64);
   constexpr uint32_t IDESC128 = umma_idesc_bf16(128, 128);
@@ -367,7 +370,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const _
   uint8_t* smem_a = smem;                                  // SA halo stages
   uint8_t* smem_b = smem_a + SA * HALO_A_STAGE;
   uint8_t* smem_c = smem_b + SB * B_STAGE_BYTES;           // [NSUB][128 rows x 64 bf16]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + NSUB * HALO_SLAB_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + CBUFS * HALO_SLAB_BYTES);
   uint64_t* full_a = bars;
   uint64_t* empty_a = bars + SA;
   uint64_t* full_b = bars + 2 * SA;
@@ -455,8 +458,8 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const _
       int sbi = 0;
       int lt = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-        const int slot = lt & 1;
-        mbar_wait(smem_u32(&bar_tempty[slot]), ((lt >> 1) & 1) ^ 1);
+        const int slot = SLOTS == 2 ? (lt & 1) : 0;
+        mbar_wait(smem_u32(&bar_tempty[slot]), ((SLOTS == 2 ? (lt >> 1) : lt) & 1) ^ 1);
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(slot * SLOT_COLS);
         uint32_t first = 1;
@@ -515,18 +518,19 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const _
 
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-      const int slot = lt & 1;
+      const int slot = SLOTS == 2 ? (lt & 1) : 0;
       const HaloTile t = decode(tile);
-      mbar_wait(smem_u32(&bar_tfull[slot]), (lt >> 1) & 1);
+      mbar_wait(smem_u32(&bar_tfull[slot]), (SLOTS == 2 ? (lt >> 1) : lt) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int sub = 0; sub < NSUB; ++sub) {   // z block zb, plane x + h: columns [sub * 64, sub * 64 + 64) of the slot
         const int zb = sub >> 1, h = sub & 1;
         const int zt0 = t.z0 + 8 * zb;
         const bool valid = (zt0 + i1 < p.d1) && (t.y0 + i2 < p.d2);
-        uint8_t* cbuf = smem_c + (size_t)sub * HALO_SLAB_BYTES;
-        if (e == 0) {   // this buffer's previous store (NSUB groups ago) has read it
-          if (NSUB == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        uint8_t* cbuf = smem_c + (size_t)(sub % CBUFS) * HALO_SLAB_BYTES;
+        if (e == 0) {   // this buffer's previous store (CBUFS groups ago) has read it
+          if (CBUFS == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          else if (CBUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
         }
         named_bar_sync(1, 128);
@@ -644,23 +648,23 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
 
-template <int SB, int CTAS_PER_SM, int ZT = 1, int SA = 1>
+template <int SB, int CTAS_PER_SM, int ZT = 1, int SA = 1, int SLOTS = 2>
 static int launch_halo_x2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const HaloParams& p,
                           cudaStream_t stream) {
-  constexpr int smem = 1024 + SA * halo_a_stage(ZT) + SB * 128 * 128 + 2 * ZT * HALO_SLAB_BYTES + (2 * SA + 2 * SB + 4) * 8 + 16 +
+  constexpr int smem = 1024 + SA * halo_a_stage(ZT) + SB * 128 * 128 + (SLOTS == 1 ? 1 : 2 * ZT) * HALO_SLAB_BYTES + (2 * SA + 2 * SB + 4) * 8 + 16 +
                        4 * 64 * 8;
   static_assert(CTAS_PER_SM * (smem + 1024) <= 228 * 1024, "shared memory budget");
-  static_assert(CTAS_PER_SM * 4 * ZT * 64 <= 512, "TMEM budget");
+  static_assert(CTAS_PER_SM * SLOTS * 2 * ZT * 64 <= 512, "TMEM budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv3_halo_x2_kernel<SB, CTAS_PER_SM, ZT, SA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv3_halo_x2_kernel<SB, CTAS_PER_SM, ZT, SA, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   int cap = persistent_sms(halo_sm_count()) * CTAS_PER_SM;
   if (cap > p.n_tiles) cap -= cap % p.n_tiles;
   const int grid = p.total_tiles < cap ? p.total_tiles : cap;
-  const cudaError_t le = launch_pdl(conv3_halo_x2_kernel<SB, CTAS_PER_SM, ZT, SA>, dim3(grid), dim3(192), smem, stream, tmA, tmB, tmC, p);
+  const cudaError_t le = launch_pdl(conv3_halo_x2_kernel<SB, CTAS_PER_SM, ZT, SA, SLOTS>, dim3(grid), dim3(192), smem, stream, tmA, tmB, tmC, p);
   count_launch();
   return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
@@ -771,9 +775,12 @@ int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
       return launch_halo_x2<4, 1, 2, 2>(tmA, tmB, tmC, p, stream);
     }
     static const int x2_variant = [] { const char* e = getenv("CTU_CONV_HALO_X2_VARIANT"); return e ? atoi(e) : 0; }();
+    // measured at 96^3 x 4, 64 -> 64 / 128 -> 64 (ms): three single-slot CTAs per SM 0.704 / 1.291; two double-slot CTAs
+    // with a 3-stage weight ring 0.725 / 1.351, with a 2-stage ring 0.770 / 1.424; one CTA per SM 1.331 / 2.555
     if (x2_variant == 1) return launch_halo_x2<4, 1>(tmA, tmB, tmC, p, stream);
     if (x2_variant == 2) return launch_halo_x2<2, 2>(tmA, tmB, tmC, p, stream);
-    return launch_halo_x2<3, 2>(tmA, tmB, tmC, p, stream);
+    if (x2_variant == 4) return launch_halo_x2<3, 2>(tmA, tmB, tmC, p, stream);
+    return launch_halo_x2<2, 3, 1, 1, 1>(tmA, tmB, tmC, p, stream);
   }
   if (d->block_n == 64) {
     if (zt == 2) return launch_halo<64, 1, 4, 2, 2>(tmA, tmB, tmC, p, stream);
