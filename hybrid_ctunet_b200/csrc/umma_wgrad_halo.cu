@@ -73,8 +73,11 @@ __device__ __forceinline__ WhItem wh_decode(const WhParams& p, int item) {
 // row offset (in 128-byte lines) of (y, z) tap t21 = ty * 3 + tz inside the halo tile
 __device__ __forceinline__ int wh_tap_off(int t21) { return (t21 / 3) * WH_Z + (t21 % 3); }
 
-template <int BN, int J, int CB, int CTAS_PER_SM, int ST>
-__global__ void __launch_bounds__(192, CTAS_PER_SM) wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX,
+// NI issuing warps (1 or 2): a tcgen05.mma of N = 64 is shorter than one thread's issue interval, so one CTA per SM with a
+// single issuer starves the tensor pipe; with NI = 2 the row tiles of an item alternate between two issuing warps (different
+// accumulators, shared operand stages).
+template <int BN, int J, int CB, int CTAS_PER_SM, int ST, int NI>
+__global__ void __launch_bounds__(160 + 32 * NI, CTAS_PER_SM) wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                       const __grid_constant__ CUtensorMap tmY,
                                                                       const WhParams p) {
   constexpr int A_BYTES = CB * WH_TILE_PITCH;
@@ -103,9 +106,9 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) wgrad_halo_kernel(const __gr
     tma_prefetch_desc(&tmY);
     for (int st = 0; st < ST; ++st) {
       mbar_init(smem_u32(&bar_full[st]), 1);
-      mbar_init(smem_u32(&bar_empty[st]), 1);
+      mbar_init(smem_u32(&bar_empty[st]), NI);
     }
-    mbar_init(smem_u32(bar_tfull), 1);
+    mbar_init(smem_u32(bar_tfull), NI);
     mbar_init(smem_u32(bar_tempty), 4);
     mbar_fence_init();
   }
@@ -147,9 +150,10 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) wgrad_halo_kernel(const __gr
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp <= NI) {
+    // ------------------------------------------------------------------ MMA issuer(s): warp 1 (and 2)
     if (lane == 0) {
+      const int iw = warp - 1;
       uint32_t it = 0;
       int li = 0;
       const uint32_t a_base0 = smem_u32(smem_a);
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) wgrad_halo_kernel(const __gr
           tc_fence_after();
           const uint32_t a_base = a_base0 + (uint32_t)(st * STAGE_BYTES);
           const uint64_t db0 = wh_desc(b_base0 + (uint32_t)(st * STAGE_BYTES), WH_SLAB_BYTES, 1024);
-          for (int mt = w.m0; mt < w.m1; ++mt) {
+          for (int mt = w.m0 + iw; mt < w.m1; mt += NI) {
             // row tile -> start offset of its first slab and the byte distance to its second slab
             uint32_t off0, lbo;
             if (CB == 1) {
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) wgrad_halo_kernel(const __gr
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (four warps after the issuers)
     const int q = warp & 3;
     const int r = q * 32 + lane;
     int li = 0;
@@ -250,7 +254,7 @@ static int wh_sm_count() {
   return n;
 }
 
-template <int BN, int J, int CB, int CTAS_PER_SM, int ST = 1>
+template <int BN, int J, int CB, int CTAS_PER_SM, int ST = 1, int NI = 1>
 static int launch_wh(const CUtensorMap& tmX, const CUtensorMap& tmY, WhParams p, int per_slot, cudaStream_t stream) {
   constexpr int smem = 1024 + ST * (CB * WH_TILE_PITCH + (BN / 64) * WH_SLAB_BYTES) + (2 * ST + 2) * 8 + 16;
   constexpr int tmem = (J * BN <= 128) ? 128 : (J * BN <= 256 ? 256 : 512);
@@ -258,7 +262,7 @@ static int launch_wh(const CUtensorMap& tmX, const CUtensorMap& tmY, WhParams p,
   static_assert(CTAS_PER_SM * tmem <= 512, "TMEM budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel<BN, J, CB, CTAS_PER_SM, ST>,
+    cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel<BN, J, CB, CTAS_PER_SM, ST, NI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
@@ -274,7 +278,7 @@ static int launch_wh(const CUtensorMap& tmX, const CUtensorMap& tmY, WhParams p,
   p.splits = splits;
   p.total_items = base * splits;
   const int grid = p.total_items < slots ? p.total_items : slots;
-  const cudaError_t le = launch_pdl(wgrad_halo_kernel<BN, J, CB, CTAS_PER_SM, ST>, dim3(grid), dim3(192), smem, stream, tmX, tmY, p);
+  const cudaError_t le = launch_pdl(wgrad_halo_kernel<BN, J, CB, CTAS_PER_SM, ST, NI>, dim3(grid), dim3(160 + 32 * NI), smem, stream, tmX, tmY, p);
   count_launch();
   return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
@@ -334,7 +338,12 @@ int wgrad_halo_dispatch(const ctu_wgrad_desc* d, cudaStream_t stream) {
       if (variant == 1) return launch_wh<64, 3, 1, 2>(tmX, tmY, p, ps, stream);
       if (variant == 2) return launch_wh<64, 5, 1, 1, 3>(tmX, tmY, p, ps1, stream);
       if (variant == 3) return launch_wh<64, 3, 1, 2, 2>(tmX, tmY, p, ps, stream);
-      return launch_wh<64, 2, 1, 4>(tmX, tmY, p, ps, stream);
+      // default: all five row tiles of an x-tap in one item, ONE CTA per SM with a three-stage ring and TWO issuing warps:
+      // a third of the L2 -> shared-memory traffic of the J = 2 shape.  64 -> 64 @96^3 x 2: 843 -> 1,027 TFLOP/s (items per
+      // CTA 2: 736, 4: 857, 6: 1,027, 8: 899, 12: 929, 16: 854); with ONE issuing warp the same shape runs at 534.
+      // Variant 6: the former four-CTA J = 2 shape.
+      if (variant == 6) return launch_wh<64, 2, 1, 4>(tmX, tmY, p, ps, stream);
+      return launch_wh<64, 5, 1, 1, 3, 2>(tmX, tmY, p, ps_env > 0 ? ps_env : 6, stream);
     }
     if (variant == 2) return launch_wh<128, 3, 1, 1, 3>(tmX, tmY, p, ps1, stream);
     return launch_wh<128, 2, 1, 2>(tmX, tmY, p, ps, stream);
@@ -342,7 +351,9 @@ int wgrad_halo_dispatch(const ctu_wgrad_desc* d, cudaStream_t stream) {
   if (d->block_n == 64) {
     if (variant == 1) return launch_wh<64, 3, 2, 2>(tmX, tmY, p, ps, stream);
     if (variant == 2) return launch_wh<64, 5, 2, 1, 3>(tmX, tmY, p, ps1, stream);
-    return launch_wh<64, 2, 2, 3>(tmX, tmY, p, ps, stream);
+    // 128 -> 64 @96^3 x 2: 805 -> 1,026 TFLOP/s with the same one-CTA, two-issuer shape (five + four row tiles per x-tap)
+    if (variant == 6) return launch_wh<64, 2, 2, 3>(tmX, tmY, p, ps, stream);
+    return launch_wh<64, 5, 2, 1, 3, 2>(tmX, tmY, p, ps_env > 0 ? ps_env : 6, stream);
   }
   // 128 -> 128: three row tiles per item on one CTA per SM with a two-stage ring (930 -> 1,129 TFLOP/s at 48x48x96 x 2);
   // variant 4: the former two-CTA J = 2 shape.  (The wide-J shapes LOSE for 64 output channels: 850 -> 534 TFLOP/s.)
