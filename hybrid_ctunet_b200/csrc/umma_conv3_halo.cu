@@ -348,8 +348,10 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_kernel(const __gr
 // 64 -> 64 @96^3 x 2 (9.6 TB/s, the L2 throughput cap; ncu), 83 % of it weights.
 // SLOTS = 1: a single accumulator slot and ONE staging buffer per CTA (72 KB of shared memory, 128 TMEM columns): three
 // CTAs per SM — the epilogue of a CTA then blocks its own main loop, the two other CTAs keep the tensor pipe fed.
-template <int SB, int CTAS_PER_SM, int ZT, int SA, int SLOTS>
-__global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const __grid_constant__ CUtensorMap tmA,
+// NI = ZT = 2: one issuing warp per z block (same operand stages, different accumulators) — one thread cannot issue N = 64
+// instructions fast enough to keep the tensor pipe busy.
+template <int SB, int CTAS_PER_SM, int ZT, int SA, int SLOTS, int NI>
+__global__ void __launch_bounds__(160 + 32 * NI, CTAS_PER_SM) conv3_halo_x2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                          const __grid_constant__ CUtensorMap tmB,
                                                                          const __grid_constant__ CUtensorMap tmC,
                                                                          const HaloParams p) {
@@ -388,9 +390,9 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const _
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
-    for (int st = 0; st < SA; ++st) { mbar_init(smem_u32(&full_a[st]), 1); mbar_init(smem_u32(&empty_a[st]), 1); }
-    for (int s = 0; s < SB; ++s) { mbar_init(smem_u32(&full_b[s]), 1); mbar_init(smem_u32(&empty_b[s]), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bar_tfull[s]), 1); mbar_init(smem_u32(&bar_tempty[s]), 4); }
+    for (int st = 0; st < SA; ++st) { mbar_init(smem_u32(&full_a[st]), 1); mbar_init(smem_u32(&empty_a[st]), NI); }
+    for (int s = 0; s < SB; ++s) { mbar_init(smem_u32(&full_b[s]), 1); mbar_init(smem_u32(&empty_b[s]), NI); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bar_tfull[s]), NI); mbar_init(smem_u32(&bar_tempty[s]), 4); }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -451,9 +453,10 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const _
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp <= NI) {
+    // ------------------------------------------------------------------ MMA issuer(s)
     if (lane == 0) {
+      const int iw = warp - 1;   // NI = 2: this warp issues for z block iw
       uint32_t ia = 0, sbph = 0;
       int sbi = 0;
       int lt = 0;
@@ -484,8 +487,10 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const _
               const uint64_t db = db0 + (uint64_t)(sbi * (B_STAGE_BYTES >> 4));
               const uint64_t da = da0 + (uint64_t)((((t21 / 3) * HALO_Z + (t21 % 3)) * 128) >> 4);
 #pragma unroll
-              for (int h = 0; h < ZT; ++h)   // the z-adjacent blocks: same weights, views 8 halo rows further
-                umma_bf16_k4(dst + (uint32_t)(h * 2 * BN), da + (uint64_t)((8 * h * 128) >> 4), db, idesc, first ? 0u : 1u);
+              for (int h = 0; h < ZT; ++h) {   // the z-adjacent blocks: same weights, views 8 halo rows further
+                if (NI == 1 || h == iw)
+                  umma_bf16_k4(dst + (uint32_t)(h * 2 * BN), da + (uint64_t)((8 * h * 128) >> 4), db, idesc, first ? 0u : 1u);
+              }
               first = 0;
               umma_commit(smem_u32(&empty_b[sbi]));
               if (++sbi == SB) { sbi = 0; sbph ^= 1u; }
@@ -498,10 +503,10 @@ __global__ void __launch_bounds__(192, CTAS_PER_SM) conv3_halo_x2_kernel(const _
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (four warps after the issuers)
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    const int e = threadIdx.x - 64;
+    const int e = threadIdx.x - 32 * (1 + NI);
     const int i1 = r & 7, i2 = r >> 3;
     float acc_s = 0.f, acc_q = 0.f;   // BN = 64 <= 128 epilogue threads: one statistics column per thread
     int stat_batch = -1;
@@ -648,7 +653,7 @@ static int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
 
-template <int SB, int CTAS_PER_SM, int ZT = 1, int SA = 1, int SLOTS = 2>
+template <int SB, int CTAS_PER_SM, int ZT = 1, int SA = 1, int SLOTS = 2, int NI = 1>
 static int launch_halo_x2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const HaloParams& p,
                           cudaStream_t stream) {
   constexpr int smem = 1024 + SA * halo_a_stage(ZT) + SB * 128 * 128 + (SLOTS == 1 ? 1 : 2 * ZT) * HALO_SLAB_BYTES + (2 * SA + 2 * SB + 4) * 8 + 16 +
@@ -657,14 +662,14 @@ static int launch_halo_x2(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   static_assert(CTAS_PER_SM * SLOTS * 2 * ZT * 64 <= 512, "TMEM budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv3_halo_x2_kernel<SB, CTAS_PER_SM, ZT, SA, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv3_halo_x2_kernel<SB, CTAS_PER_SM, ZT, SA, SLOTS, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   int cap = persistent_sms(halo_sm_count()) * CTAS_PER_SM;
   if (cap > p.n_tiles) cap -= cap % p.n_tiles;
   const int grid = p.total_tiles < cap ? p.total_tiles : cap;
-  const cudaError_t le = launch_pdl(conv3_halo_x2_kernel<SB, CTAS_PER_SM, ZT, SA, SLOTS>, dim3(grid), dim3(192), smem, stream, tmA, tmB, tmC, p);
+  const cudaError_t le = launch_pdl(conv3_halo_x2_kernel<SB, CTAS_PER_SM, ZT, SA, SLOTS, NI>, dim3(grid), dim3(160 + 32 * NI), smem, stream, tmA, tmB, tmC, p);
   count_launch();
   return le != cudaSuccess ? (int)le : (int)cudaGetLastError();
 }
@@ -696,9 +701,13 @@ int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
   static const int x2_mode = [] { const char* e = getenv("CTU_CONV_HALO_X2"); return e ? atoi(e) : 1; }();
   const bool x2 = x2_mode != 0 && d->block_n == 64 && d->w_x3 != nullptr && d->d3 % 2 == 0 && zt == 1 &&
                   !(d->a_c == 64 && d->a_c_live > 0 && d->a_c_live < 64);
-  // CTU_CONV_HALO_X2_ZT=2 (opt-in): two z blocks per tile on ONE CTA per SM (TMEM 512 columns): 43 % less L2 -> shared-memory
-  // traffic, but measured SLOWER (64->64 @96^3 x 4: 0.764 vs 0.706 ms; 128->64 1.435 vs 1.324) — one issuing thread and one
-  // epilogue per SM lose more than the traffic saves, as with every one-CTA-per-SM shape tried in this file.
+  // Two z blocks per tile on ONE CTA per SM (TMEM 512 columns, 43 % less L2 -> shared-memory traffic) with TWO issuing warps,
+  // one per z block: 64->64 @96^3 x 4 0.654 ms (1,198 TFLOP/s), 128->64 1.238 ms, against 0.695 / 1.285 for three single-slot
+  // CTAs per SM (CTU_CONV_HALO_X2_ZT=1, also the shape for z extents that are not multiples of 16) and 0.764 / 1.435 for the
+  // same tile with ONE issuing warp (CTU_CONV_HALO_X2_NI=1): a tcgen05.mma of N = 64 is shorter than a thread's issue interval.
+  // Stand-alone the ZT = 2 shape is the fastest; inside the two-lane CUDA graph it is not (conv class 12.12 vs 11.89 ms per
+  // training step, inference 26.20 vs 25.89 ms per 4 windows): a 218 KB CTA leaves no room for the other lane's kernels on the
+  // SM, three 72 KB CTAs do.  Opt-in: CTU_CONV_HALO_X2_ZT=2.
   static const int x2_zt = [] { const char* e = getenv("CTU_CONV_HALO_X2_ZT"); return e ? atoi(e) : 1; }();
   const int zt_box = (x2 && x2_zt == 2 && d->d1 % 16 == 0) ? 2 : zt;   // z blocks per tile (halo box 18 instead of 10 deep)
   CUtensorMap tmA, tmB, tmC;
@@ -772,6 +781,8 @@ int conv3_halo_dispatch(const ctu_gemm_desc* d, cudaStream_t stream) {
     if (zt_box == 2) {
       p.T1 = d->d1 / 16;
       p.total_tiles /= 2;
+      static const int zt_ni = [] { const char* e = getenv("CTU_CONV_HALO_X2_NI"); return e ? atoi(e) : 2; }();
+      if (zt_ni == 2) return launch_halo_x2<4, 1, 2, 2, 2, 2>(tmA, tmB, tmC, p, stream);
       return launch_halo_x2<4, 1, 2, 2>(tmA, tmB, tmC, p, stream);
     }
     static const int x2_variant = [] { const char* e = getenv("CTU_CONV_HALO_X2_VARIANT"); return e ? atoi(e) : 0; }();

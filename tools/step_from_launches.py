@@ -12,10 +12,10 @@ lo = max(i for i, (n, _) in enumerate(seq) if n.startswith("pack_weights_kernel"
 step = seq[lo:hi]
 tot = sum(t for _, t in step)
 print(f"one training step (launches {lo}..{hi}): {len(step)} launches, {tot / 1e3:.2f} ms of kernels serialised")
-CLASSES = [("tcgen05 conv/gemm/dgrad", ("umma_gemm_kernel", "conv3_halo_kernel")), ("tcgen05 wgrad", ("umma_wgrad_kernel", "wgrad_halo_kernel")),
-           ("InstanceNorm", ("in_",)), ("attention", ("attention",)), ("LayerNorm", ("layernorm", "patchify")),
+CLASSES = [("tcgen05 conv/gemm/dgrad", ("umma_gemm_kernel", "conv3_halo_kernel", "conv3_halo_x2_kernel", "ffn_fused_kernel")), ("tcgen05 wgrad", ("umma_wgrad_kernel", "wgrad_halo_kernel")),
+           ("InstanceNorm", ("in_", "stats_fold")), ("attention", ("attention",)), ("LayerNorm", ("layernorm", "patchify")),
            ("pack/unpack/AdamW", ("pack_weights", "unpack_grads", "adamw")), ("gelu/pwa", ("gelu", "pwa_")),
-           ("loss", ("dice_ce",)),
+           ("loss", ("dice_ce", "gather3d")),
            ("colsum/accumulate/cast/layout", ("colsum", "accumulate", "cast_", "space_to_depth", "cf_to_cl", "subsample", "im2col", "conv_cin1")),
            ("head backward (fused CUDA-core)", ("head_bwd",))]
 cl = collections.OrderedDict((c, 0.0) for c, _ in CLASSES)
