@@ -62,6 +62,7 @@ PACK_LIN, PACK_LIN_T, PACK_CONV3, PACK_CONV3_T, PACK_CONVT, PACK_CONVT_T, PACK_P
 _PAIR_L1 = os.environ.get("CTU_PAIR_L1", "1") != "0"
 # 64-output-channel 3x3x3 convolutions on the kernel that computes two x-planes per tile (needs a re-laid weight copy)
 _HALO_X2 = os.environ.get("CTU_CONV_HALO_X2", "1") != "0"
+_TUNET_LANES = os.environ.get("CTU_TUNET_LANES", "1") != "0"
 _ITEM_DTYPE = np.dtype([("src", "u8"), ("dst", "u8"), ("kind", "i4"), ("rows", "i4"), ("cols", "i4"), ("a", "i4"),
                         ("b", "i4"), ("c", "i4"), ("unit0", "i8")])
 
@@ -1375,7 +1376,13 @@ class Engine:
     def tunet(self, x_in, pf: int, depth: int = 12, heads: int = 12):
         """TUNet.forward (hybrid_CTUNet.py:1021-1036)."""
         self.stats.reset()
-        _, vit_logits, vit_96 = self._vit_branch(x_in, pf, depth, heads)
+        # inference under CUDA-graph capture: vit_encoder0 (GPU-filling 96^3 kernels, independent of the transformer until
+        # the concat) on a second stream beside the transformer's long run of small kernels — TUNet has no ResNet lane to
+        # fill the idle SMs otherwise (CTU_TUNET_LANES=0 switches it off)
+        lane2 = None
+        if self.two_lanes and _TUNET_LANES and self.tape is None and torch.cuda.is_current_stream_capturing():
+            lane2 = self._side2_stream()
+        _, vit_logits, vit_96 = self._vit_branch(x_in, pf, depth, heads, lane2=lane2)
         return (vit_logits, vit_96)
 
     def up_cat_conv(self, pre: str, inp, skip, cout: int):
