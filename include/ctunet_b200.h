@@ -346,6 +346,15 @@ int ctu_dice_ce_finalize(const ctu_loss_heads* heads, const double* sums, float*
 int ctu_gather3d(const float* src, float* dst, int B, int X, int Y, int Z, int Xo, int Yo, int Zo, const int* ix,
                  const int* iy, const int* iz, void* stream);
 
+/* Post-processing of a predicted label volume (test_CTUNet_final.py:132-190, remove_all_but_the_largest_connected_component,
+ * one class or class group per call): the voxels whose label is in the set `member` (uint8 [256], non-zero = member) are
+ * split into connected components (6-connectivity = scipy.ndimage.label's default structure); every component that is not
+ * (one of) the largest — and, with has_min, whose size count * volume_per_voxel is < min_valid (float64, as the reference
+ * compares) — is set to 0 in `image` (uint8 [X][Y][Z], in place).  Scratch: parent, sizes int32 [X*Y*Z]; summary int32 [4] =
+ * (number of components, voxels of the largest, voxels of the largest one removed, 0).  X*Y*Z < 2^31. */
+int ctu_cc_filter_largest(uint8_t* image, const uint8_t* member, int X, int Y, int Z, double volume_per_voxel, int has_min,
+                          double min_valid, int* parent, int* sizes, int* summary, void* stream);
+
 /* Multi-tensor AdamW: the optimizer step of main_CTUNet.py:190-193 (torch.optim.AdamW(lr, weight_decay), no amsgrad) as
  * ONE launch over a device-resident item table — one item per parameter that has a gradient; all four tensors fp32 and
  * contiguous, numel elements each; unit0 = index of the item's first work unit (1024 elements per unit), items sorted by

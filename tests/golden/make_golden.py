@@ -198,7 +198,29 @@ def resnet_stages():
     save("resnet101_stages_32", **arrs, **probe_np(m))
 
 
+def postprocess_ref():
+    """tests/golden/postprocess_ref.npz: the reference's remove_all_but_the_largest_connected_component
+    (test_CTUNet_final.py:132-190, executed unmodified through oracle/ref_exec.py) on the synthetic label volumes of
+    tests/test_postprocess_cpu.py::CASES."""
+    from copy import deepcopy
+    from scipy.ndimage import label
+    from oracle import postprocess_oracle as PO
+    from oracle import ref_exec
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from test_postprocess_cpu import CASES
+    ref = ref_exec.extract("test_CTUNet_final.py", ["remove_all_but_the_largest_connected_component"],
+                           extra_globals=dict(deepcopy=deepcopy, label=label))["remove_all_but_the_largest_connected_component"]
+    d = {}
+    for i, (shape, classes, vpv, mins) in enumerate(CASES):
+        img = PO.blob_volume(shape, seed=i)
+        out, rem, kept = ref(img, classes, vpv, mins)
+        d[f"in{i}"], d[f"out{i}"] = img, out
+        d[f"removed{i}"], d[f"kept{i}"] = np.array(rem, dtype=object), np.array(kept, dtype=object)
+    np.savez_compressed(os.path.join(HERE, "postprocess_ref.npz"), **d)
+
+
 if __name__ == "__main__":
+    postprocess_ref()
     sliding_window_ref()
     resnet_stages()
     if "--only-new" in sys.argv:

@@ -19,7 +19,7 @@ def test_header_declares_the_hot_path_entry_points():
                  "ctu_umma_wgrad", "ctu_in_bwd_stats", "ctu_in_bwd_apply", "ctu_layernorm_bwd", "ctu_attention_bwd",
                  "ctu_pwa_fuse_bwd", "ctu_gelu_bwd", "ctu_colsum", "ctu_accumulate", "ctu_pack_weights", "ctu_unpack_grads",
                  "ctu_dice_ce_fwd", "ctu_dice_ce_bwd", "ctu_ensemble_argmax", "ctu_adamw_step",
-                 "ctu_set_persistent_sm_limit", "ctu_ffn_fused", "ctu_dice_ce_finalize", "ctu_gather3d"):
+                 "ctu_set_persistent_sm_limit", "ctu_ffn_fused", "ctu_dice_ce_finalize", "ctu_gather3d", "ctu_cc_filter_largest", "ctu_stats_fold"):
         assert must in names
 
 
