@@ -16,7 +16,7 @@ import torch
 
 from . import lib as _lib
 
-__all__ = ["remove_all_but_the_largest_connected_component"]
+__all__ = ["remove_all_but_the_largest_connected_component", "determine_postprocessing", "com_dice", "dice"]
 
 
 def _key(c):
@@ -73,3 +73,74 @@ def remove_all_but_the_largest_connected_component(image_in, for_which_classes, 
     if is_np:
         return out.cpu().numpy().astype(image_in.dtype, copy=False), largest_removed, kept_size
     return (out if src.is_cuda else out.cpu()), largest_removed, kept_size
+
+
+def dice(x, y) -> float:
+    """utils/utils.py:16-22 on boolean masks (numpy arrays or torch tensors): 2 |x y| / (|x| + |y|), 0.0 for an empty
+    label mask.  Integer counts, the reference's float64 division."""
+    if isinstance(x, torch.Tensor) or isinstance(y, torch.Tensor):
+        x = torch.as_tensor(x)
+        y = torch.as_tensor(y, device=x.device)
+        inter, xs, ys = int((x & y).sum()), int(x.sum()), int(y.sum())
+    else:
+        inter, xs, ys = int(np.sum(x * y)), int(np.sum(x)), int(np.sum(y))
+    if ys == 0:
+        return 0.0
+    return 2 * inter / (xs + ys)
+
+
+def com_dice(infers, labels, classes: Sequence[int] = tuple(range(1, 14))) -> np.ndarray:
+    """test_CTUNet_final.py:106-117: per-class Dice averaged over the cases."""
+    rows = [[dice(infers[i] == j, labels[i] == j) for j in classes] for i in range(len(labels))]
+    return np.mean(rows, 0)
+
+
+def determine_postprocessing(infers, labels, volume_per_voxel, dice_threshold: float = 0.0, processes: int = 8,
+                             advanced_postprocessing: bool = False, _remove=None):
+    """test_CTUNet_final.py:192-401: decide, on a set of cases, for which classes "keep only the largest connected
+    component" improves the mean Dice (first all foreground classes as one region, then every class on its own, optionally
+    with size thresholds learnt from the cases), then apply that rule to every case.  Returns the list of post-processed
+    volumes like the reference (`processes` is accepted and ignored: the per-case work runs on the GPU, not in a host pool).
+    `_remove`: the component filter to use (tests inject the host oracle)."""
+    remove = _remove or remove_all_but_the_largest_connected_component
+    classes = list(range(1, 14))
+    n = len(labels)
+    for_which_classes: list = []
+    min_valid_object_sizes: Optional[dict] = {}
+
+    def learn_min_sizes(sources, which):
+        kept_min: dict = {}
+        for i in range(n):
+            _, _, kept = remove(sources[i], which, volume_per_voxel[i], None)
+            for k, v in kept.items():
+                if v is not None:
+                    kept_min[k] = v if kept_min.get(k) is None else min(kept_min[k], v)
+        return kept_min
+
+    # 1. all foreground classes as one region (:208-281)
+    min_size_kept = learn_min_sizes(infers, (classes,)) if advanced_postprocessing else None
+    infers_pp = [remove(infers[i], (classes,), volume_per_voxel[i], min_size_kept)[0] for i in range(n)]
+    raw = com_dice(infers, labels)
+    pp_all = com_dice(infers_pp, labels)
+    do_fg_cc = False
+    if any(pp_all[i] > raw[i] + dice_threshold for i in range(len(classes))):
+        if not any(pp_all[i] < raw[i] for i in range(len(classes))):
+            for_which_classes.append(classes)
+            if min_size_kept is not None:
+                min_valid_object_sizes.update(dict(min_size_kept))
+            do_fg_cc = True
+    # 2. every class on its own, on top of step 1 if that was adopted (:296-371)
+    source = infers_pp if do_fg_cc else infers
+    min_size_kept = learn_min_sizes(source, classes) if advanced_postprocessing else None
+    infers_pp_new = [remove(source[i], classes, volume_per_voxel[i], min_size_kept)[0] for i in range(n)]
+    old_res = pp_all if do_fg_cc else raw
+    pp_cls = com_dice(infers_pp_new, labels)
+    for i, cl in enumerate(classes):
+        if pp_cls[i] > old_res[i] + dice_threshold:
+            for_which_classes.append(int(cl))
+            if min_size_kept is not None:
+                min_valid_object_sizes.update({cl: min_size_kept[cl]})
+    if not advanced_postprocessing:
+        min_valid_object_sizes = None
+    # 3. apply the rule (:387-399)
+    return [remove(infers[i], for_which_classes, volume_per_voxel[i], min_valid_object_sizes)[0] for i in range(n)]

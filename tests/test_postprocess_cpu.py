@@ -53,3 +53,64 @@ def test_every_largest_object_is_kept_and_nothing_else_changes():
     out, removed, kept = PO.remove_all_but_the_largest_connected_component(img, [1], 2.0)
     assert out[3, 3, 3] == 0 and (out[0, 0, :3] == 1).all() and (out[5, 5, 3:] == 1).all() and (out[2, :, 0] == 2).all()
     assert removed == {1: 2.0} and kept == {1: 6.0}
+
+
+def _pp_cases():
+    """Three "cases" (prediction, label, voxel volume): the label plus spurious blobs / holes, so that the largest-component
+    rule improves some classes and not others."""
+    cases = []
+    for seed, shape, vpv in ((11, (20, 22, 18), 1.0), (12, (18, 18, 24), 2.0), (13, (22, 16, 20), 0.5)):
+        lab = np.zeros(shape, dtype=np.int64)
+        rng = np.random.default_rng(seed)
+        for c in range(1, 14):                      # one box per class
+            lo = rng.integers(0, np.array(shape) - 6)
+            lab[lo[0]:lo[0] + 5, lo[1]:lo[1] + 5, lo[2]:lo[2] + 5] = c
+        inf = lab.copy()
+        noise = PO.blob_volume(shape, n_classes=13, seed=seed + 100, density=0.62)
+        m = (inf == 0) & (noise > 0) & (rng.random(shape) < 0.35)
+        inf[m] = noise[m]
+        cases.append((inf, lab, vpv))
+    return [c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases]
+
+
+class _SyncPool:
+    """multiprocessing.pool.Pool stand-in for the reference's determine_postprocessing (test_CTUNet_final.py:197)."""
+    def __init__(self, *_a, **_k):
+        pass
+
+    def starmap_async(self, fn, iterable):
+        res = [fn(*args) for args in iterable]
+
+        class R:
+            def get(self_inner):
+                return res
+        return R()
+
+    def close(self):
+        pass
+
+    def join(self):
+        pass
+
+
+@pytest.mark.skipif(not ref_exec.available(), reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("advanced", [False, True])
+def test_determine_postprocessing_equals_the_reference(advanced):
+    """hybrid_ctunet_b200.postprocess.determine_postprocessing (control flow restated, component filter injected = the
+    host oracle) against the reference's function executed unmodified with a synchronous pool."""
+    import contextlib
+    import io
+    from copy import deepcopy
+    from scipy.ndimage import label
+    from hybrid_ctunet_b200 import postprocess as P
+    ns = dict(deepcopy=deepcopy, label=label, Pool=_SyncPool, dice=P.dice)
+    fns = ref_exec.extract("test_CTUNet_final.py", ["remove_all_but_the_largest_connected_component", "determine_postprocessing",
+                                                    "com_dice"], extra_globals=ns)
+    infers, labels, vpv = _pp_cases()
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = fns["determine_postprocessing"](infers, labels, vpv, 0.0, 2, advanced)
+    ours = P.determine_postprocessing(infers, labels, vpv, 0.0, 2, advanced,
+                                      _remove=PO.remove_all_but_the_largest_connected_component)
+    assert len(ref) == len(ours) and any((r != i).any() for r, i in zip(ref, infers))
+    for r, o in zip(ref, ours):
+        assert np.array_equal(r, o)

@@ -52,3 +52,19 @@ def test_full_volume_properties():
     assert kept[fg] == float((out > 0).sum()) and removed[fg] is not None and removed[fg] < kept[fg]
     out2, removed2, kept2 = ours(out, [fg], 1.0)
     assert torch.equal(out2, out) and removed2[fg] is None and kept2[fg] == kept[fg]
+
+
+@pytest.mark.parametrize("advanced", [False, True])
+def test_determine_postprocessing_on_the_device_equals_the_host_flow(advanced):
+    """determine_postprocessing with the CUDA component filter == the same flow with the scipy oracle injected (which
+    tests/test_postprocess_cpu.py pins against the reference's own function, test_CTUNet_final.py:192-401)."""
+    from hybrid_ctunet_b200 import postprocess as P
+    from oracle import postprocess_oracle as PO
+    from test_postprocess_cpu import _pp_cases
+    infers, labels, vpv = _pp_cases()
+    ours = P.determine_postprocessing(infers, labels, vpv, 0.0, 8, advanced)
+    host = P.determine_postprocessing(infers, labels, vpv, 0.0, 8, advanced,
+                                      _remove=PO.remove_all_but_the_largest_connected_component)
+    assert any((o != i).any() for o, i in zip(ours, infers))
+    for o, h in zip(ours, host):
+        assert o.dtype == h.dtype and np.array_equal(o, h)
