@@ -49,6 +49,7 @@ struct GemmParams {
   int stats_ld, out_col0;
   int tma_store;
   int fast;  // bf16 rows through the TMA store (any activation, no fp32 residual): the epilogue takes the lean chunk
+  int stage_res;  // fast path, flat rows, bf16 residual-like operand: staged through the output staging tile (cp.async)
 };
 
 struct TileCoord {
@@ -276,9 +277,41 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, CTAS_PER_SM) umma_gemm_ke
                                 ((long long)v1 * p.u1 + a1);
       uint8_t* cbuf = smem_c + (size_t)(OUT_BUFS > 0 ? (lt % (OUT_BUFS > 0 ? OUT_BUFS : 1)) : 0) * SLABS * SLAB_BYTES;
 
+      // Residual-like operand (a gradient that has already arrived, or the pre-activation of a GELU) of a flat-row GEMM:
+      // staged into the output staging tile with COALESCED 16-byte async copies while the accumulator is still being
+      // computed — a thread reading its own row straight from global memory costs 32 L1 wavefronts per load instruction
+      // (2,048 per 128 x 128 tile), which bounds the +res / +gelu_bwd shapes at 2.0-2.9 TB/s.
+      bool stage_res = false;
+      if constexpr (CH == 32 && SLABS > 0) {
+        stage_res = p.stage_res != 0 && use_tma;
+        if (stage_res) {
+          if (e == 0) {
+            if (OUT_BUFS > 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          named_bar_sync(1, EPI_THREADS);
+          constexpr int CHUNKS_PER_ROW = BN / 8;                       // 16-byte chunks of one tile row
+          const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                       ((long long)tc.t4 * p.d1 + tc.x1) * p.ldr + p.out_col0 + n0;
+#pragma unroll
+          for (int id = e; id < BLOCK_M * CHUNKS_PER_ROW; id += EPI_THREADS) {
+            const int rr = id / CHUNKS_PER_ROW, c16 = id % CHUNKS_PER_ROW;
+            if (tc.x1 + rr < p.d1 && n0 + c16 * 8 < p.n_real) {
+              const uint32_t dst = smem_u32(cbuf) + (uint32_t)((c16 >> 3) * SLAB_BYTES + rr * 128 + (((c16 & 7) ^ (rr & 7)) << 4));
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rbase + (long long)rr * p.ldr + c16 * 8)
+                           : "memory");
+            }
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+      }
+
       mbar_wait(smem_u32(&bar_tfull[slot]), uph);
       tc_fence_after();
-      if (sync_tiles) {
+      if (stage_res) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        named_bar_sync(1, EPI_THREADS);
+      } else if (sync_tiles) {
         // the staging buffer about to be overwritten must have been read by its TMA store (OUT_BUFS tiles ago),
         // and every thread must be done with the previous tile's statistics scratch
         if (use_tma && e == 0) {
@@ -466,11 +499,20 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, CTAS_PER_SM) umma_gemm_ke
             if (p.res_mode != CTU_RES_NONE && valid) {
               // bf16 rows shaped like the output: a gradient that has already arrived (added), or the pre-activation of
               // the GELU whose derivative scales this input gradient
-              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
-                                                               out_row * p.ldr + p.out_col0 + colbase + c0);
               uint4 rv[4];
+              if (stage_res) {   // this thread's row of the staged tile (same swizzled positions the result goes back to)
+                const uint32_t rb = smem_u32(cbuf) + (uint32_t)((c0 >> 6) * SLAB_BYTES + r * 128);
+                const int cbk = (c0 & 63) >> 3;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) rv[i] = rp[i];
+                for (int i = 0; i < 4; ++i)
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rv[i].x), "=r"(rv[i].y), "=r"(rv[i].z), "=r"(rv[i].w)
+                               : "r"(rb + (uint32_t)(((cbk + i) ^ (r & 7)) << 4)) : "memory");
+              } else {
+                const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                                                 out_row * p.ldr + p.out_col0 + colbase + c0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rv[i] = rp[i];
+              }
               const bool gelu_bwd = p.res_mode == CTU_RES_GELU_BWD;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -750,6 +792,10 @@ extern "C" int ctu_umma_gemm(const ctu_gemm_desc* d, void* stream_) {
   p.stats_ld = d->stats_ld; p.out_col0 = d->out_col0;
   p.tma_store = tma_store ? 1 : 0;
   p.fast = (tma_store && d->res_mode != CTU_RES_F32) ? 1 : 0;
+  static const int stage_env = [] { const char* e = getenv("CTU_GEMM_STAGE_RES"); return e ? atoi(e) : 1; }();
+  p.stage_res = (stage_env && p.fast && (d->res_mode == CTU_RES_BF16 || d->res_mode == CTU_RES_GELU_BWD) && d->b1 == BLOCK_M &&
+                 d->d2 == 1 && d->d3 == 1 && d->n_real % 8 == 0 && d->k1 == 1 &&
+                 (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0) ? 1 : 0;
   const long long tiles_ll = (long long)p.T1 * p.T2 * p.T3 * d->d4 * p.n_tiles;
   if (tiles_ll <= 0 || tiles_ll > 0x7fffffffLL) return CTU_E_BADARG;
   p.total_tiles = (int)tiles_ll;
