@@ -272,7 +272,8 @@ static int launch_wh(const CUtensorMap& tmX, const CUtensorMap& tmY, WhParams p,
   const int base = 3 * p.SG * p.NT;
   static const int forced = [] { const char* e = getenv("CTU_WGRAD_ITEMS_PER_SLOT"); return e ? atoi(e) : 0; }();
   if (forced > 0) per_slot = forced;
-  int splits = (per_slot * slots + base - 1) / base;
+  int splits = (per_slot * slots) / base;   // rounded DOWN: base * splits <= per_slot * slots, i.e. no CTA gets one item more
+                                            // than the others (rounding up left e.g. 891 items on 148 CTAs: 7 vs 6)
   if (splits > p.vox_tiles) splits = p.vox_tiles;
   if (splits < 1) splits = 1;
   p.splits = splits;
