@@ -63,6 +63,7 @@ _PAIR_L1 = os.environ.get("CTU_PAIR_L1", "1") != "0"
 # 64-output-channel 3x3x3 convolutions on the kernel that computes two x-planes per tile (needs a re-laid weight copy)
 _HALO_X2 = os.environ.get("CTU_CONV_HALO_X2", "1") != "0"
 _TUNET_LANES = os.environ.get("CTU_TUNET_LANES", "1") != "0"
+_CIN1_TC = os.environ.get("CTU_CIN1_TC", "1") != "0"   # vit_encoder0 conv1 (1 -> 64, k3) on the tensor cores via im2col
 _ITEM_DTYPE = np.dtype([("src", "u8"), ("dst", "u8"), ("kind", "i4"), ("rows", "i4"), ("cols", "i4"), ("a", "i4"),
                         ("b", "i4"), ("c", "i4"), ("unit0", "i8")])
 
@@ -1228,9 +1229,18 @@ class Engine:
     def res_block_cin1(self, pre: str, x_in, out=None):
         """ResBlock(1 -> 64) of vit_encoder0 (hybrid_CTUNet.py:786-793): conv1/conv3 have one input channel."""
         B, _, X, Y, Z = x_in.shape
-        c1 = self.conv_cin1(x_in, pre + ".conv1.conv", self._empty(B, X, Y, Z, 64), k=(3, 3, 3), s=(1, 1, 1), p=(1, 1, 1))
         st1 = self.stats.take(B, 64)
-        ops.in_stats(c1, st1)
+        if _CIN1_TC:
+            # k3 (27 taps) like the stem: single-channel im2col (taps zero-padded to 64 columns) + tensor-core GEMM with the
+            # InstanceNorm statistics in its epilogue — no separate statistics pass, and the column matrix is kept for the
+            # weight gradient instead of being rebuilt in the backward pass
+            col = self._empty(B, X, Y, Z, 64)
+            ops.im2col_cin1(x_in, col, k=(3, 3, 3), s=(1, 1, 1), p=(1, 1, 1))
+            c1 = self.gemm(col, "cin1", pre + ".conv1.conv", self._empty(B, X, Y, Z, 64), dims=(Z, Y, X, B), stats=st1,
+                           a_needs_grad=False)
+        else:
+            c1 = self.conv_cin1(x_in, pre + ".conv1.conv", self._empty(B, X, Y, Z, 64), k=(3, 3, 3), s=(1, 1, 1), p=(1, 1, 1))
+            ops.in_stats(c1, st1)
         a1 = self.in_apply(c1, st1)
         st2 = self.stats.take(B, 64)
         c2 = self.conv3x3(a1, pre + ".conv2.conv", st2)
