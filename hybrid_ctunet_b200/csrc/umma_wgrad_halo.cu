@@ -344,7 +344,7 @@ int wgrad_halo_dispatch(const ctu_wgrad_desc* d, cudaStream_t stream) {
       // CTA 2: 736, 4: 857, 6: 1,027, 8: 899, 12: 929, 16: 854); with ONE issuing warp the same shape runs at 534.
       // Variant 6: the former four-CTA J = 2 shape.
       if (variant == 6) return launch_wh<64, 2, 1, 4>(tmX, tmY, p, ps, stream);
-      return launch_wh<64, 5, 1, 1, 3, 2>(tmX, tmY, p, ps_env > 0 ? ps_env : 6, stream);
+      return launch_wh<64, 5, 1, 1, 3, 2>(tmX, tmY, p, ps_env > 0 ? ps_env : 3, stream);   // after the split-rounding fix: 3: 1,078, 4: 1,061, 6: 1,030
     }
     if (variant == 2) return launch_wh<128, 3, 1, 1, 3>(tmX, tmY, p, ps1, stream);
     return launch_wh<128, 2, 1, 2>(tmX, tmY, p, ps, stream);
@@ -354,12 +354,12 @@ int wgrad_halo_dispatch(const ctu_wgrad_desc* d, cudaStream_t stream) {
     if (variant == 2) return launch_wh<64, 5, 2, 1, 3>(tmX, tmY, p, ps1, stream);
     // 128 -> 64 @96^3 x 2: 805 -> 1,026 TFLOP/s with the same one-CTA, two-issuer shape (five + four row tiles per x-tap)
     if (variant == 6) return launch_wh<64, 2, 2, 3>(tmX, tmY, p, ps, stream);
-    return launch_wh<64, 5, 2, 1, 3, 2>(tmX, tmY, p, ps_env > 0 ? ps_env : 6, stream);
+    return launch_wh<64, 5, 2, 1, 3, 2>(tmX, tmY, p, ps_env > 0 ? ps_env : 4, stream);
   }
   // 128 -> 128: three row tiles per item on one CTA per SM with a two-stage ring (930 -> 1,129 TFLOP/s at 48x48x96 x 2);
   // variant 4: the former two-CTA J = 2 shape.  (The wide-J shapes LOSE for 64 output channels: 850 -> 534 TFLOP/s.)
   if (variant == 4) return launch_wh<128, 2, 2, 2>(tmX, tmY, p, ps, stream);
-  return launch_wh<128, 3, 2, 1, 2>(tmX, tmY, p, ps_env > 0 ? ps_env : 6, stream);   // 4: 1,100, 6: 1,129, 8: 1,088, 16: 971 TFLOP/s
+  return launch_wh<128, 3, 2, 1, 2>(tmX, tmY, p, ps_env > 0 ? ps_env : 3, stream);   // items per CTA (after the split-rounding fix) 3: 1,351, 4: 1,312, 5: 1,286, 6: 1,249, 8: 1,198 TFLOP/s
 }
 
 }  // namespace ctu
