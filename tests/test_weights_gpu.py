@@ -113,3 +113,108 @@ def test_mixed_table_matches_single_item_runs():
         assert torch.equal(o, together[i])
     assert torch.equal(together[0], w1.t().to(BF))
     assert torch.equal(together[3], w3.reshape(128, 64, 8).permute(2, 1, 0).reshape(8 * 64, 128).to(BF))
+
+
+# ------------------------------------------------------------------------------------------------ paired layouts
+def _paired_conv3_weight(w):
+    """Dense [2 co][27 (pair taps)][2 ci] weight of the 3x3x3 convolution over PAIRED rows (two z-neighbours per row, slot =
+    z & 1) built from the definition: output slot s_out at pair position p sees input slot s_in at pair position p + pz - 1
+    through the real z tap dz = 2 (pz - 1) + s_in - s_out."""
+    co, ci = w.shape[:2]
+    big = torch.zeros(2, co, 3, 3, 3, 2, ci, device=w.device)      # [s_out][o][tx][ty][pz][s_in][i]
+    for s_out in range(2):
+        for s_in in range(2):
+            for pz in range(3):
+                dz = 2 * (pz - 1) + s_in - s_out
+                if -1 <= dz <= 1:
+                    big[s_out, :, :, :, pz, s_in, :] = w[:, :, :, :, dz + 1].permute(0, 2, 3, 1)
+    return big.reshape(2 * co, 27, 2 * ci)
+
+
+@pytest.mark.parametrize("co,ci", [(32, 32), (32, 64), (128, 32), (32, 128)])
+def test_pack_paired_layouts(co, ci):
+    """CTU_PACK_PAIR_LIN / _T (block-diagonal 1x1x1) and CTU_PACK_PAIR_CONV3 / _T (pair-tap 3x3x3) against their definitions
+    (ResNet layer-1 bottlenecks on paired rows, resnet.py:181-186)."""
+    from hybrid_ctunet_b200 import engine as E
+    torch.manual_seed(co + 7 * ci)
+    w1 = torch.randn(co, ci, device="cuda")
+    lin = torch.full((2 * co, 2 * ci), 7.0, device="cuda", dtype=BF)
+    lin_t = torch.full((2 * ci, 2 * co), 7.0, device="cuda", dtype=BF)
+    t = _table()
+    t.add(w1.data_ptr(), lin.data_ptr(), E.PACK_PAIR_LIN, 2 * co, 2 * ci, co, ci, 0)
+    t.add(w1.data_ptr(), lin_t.data_ptr(), E.PACK_PAIR_LIN_T, 2 * ci, 2 * co, co, ci, 0)
+    if co == ci == 32:
+        w3 = torch.randn(co, ci, 3, 3, 3, device="cuda")
+        c3 = torch.full((2 * co, 27 * 2 * ci), 7.0, device="cuda", dtype=BF)
+        c3_t = torch.full((2 * ci, 27 * 2 * co), 7.0, device="cuda", dtype=BF)
+        t.add(w3.data_ptr(), c3.data_ptr(), E.PACK_PAIR_CONV3, 2 * co, 27 * 2 * ci, co, ci, 0)
+        t.add(w3.data_ptr(), c3_t.data_ptr(), E.PACK_PAIR_CONV3_T, 2 * ci, 27 * 2 * co, co, ci, 0)
+    t.run("ctu_pack_weights")
+    ref = torch.block_diag(w1, w1)
+    assert torch.equal(lin, ref.to(BF)) and torch.equal(lin_t, ref.t().contiguous().to(BF))
+    if co == ci == 32:
+        big = _paired_conv3_weight(w3)                                   # [n][ptap][k]
+        assert torch.equal(c3, big.reshape(2 * co, -1).to(BF))
+        assert torch.equal(c3_t, big.flip(1).permute(2, 1, 0).reshape(2 * ci, -1).to(BF))   # tap-flipped transpose
+
+
+def test_paired_conv_equals_the_plain_conv():
+    """The pair-tap weight applied to paired rows IS the 3x3x3 convolution: F.conv3d on [B, 32, X, Y, Z] against F.conv3d
+    with the paired weight on the [B, 64, X, Y, Z/2] view (fp32, no kernels of this library: pins the layout definition)."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    w = torch.randn(32, 32, 3, 3, 3, device="cuda")
+    x = torch.randn(2, 32, 5, 6, 8, device="cuda")
+    ref = F.conv3d(x, w, padding=1)
+    big = _paired_conv3_weight(w).reshape(64, 3, 3, 3, 64).permute(0, 4, 1, 2, 3)        # [n][k][tx][ty][pz]
+    pair = lambda t: t.reshape(2, 32, 5, 6, 4, 2).permute(0, 5, 1, 2, 3, 4).reshape(2, 64, 5, 6, 4)   # channel = slot * 32 + c
+    out = F.conv3d(pair(x), big, padding=1)
+    assert torch.allclose(out, pair(ref), atol=2e-3, rtol=1e-4)   # |out| ~ 30: fp32 summation order only
+
+
+def test_unpack_paired_gradients():
+    """ctu_unpack_grads kinds PAIR_LIN / PAIR_CONV3: the real weight's gradient is the sum of the blocks of the paired
+    weight's gradient that hold it."""
+    from hybrid_ctunet_b200 import engine as E
+    torch.manual_seed(3)
+    co, ci = 32, 64
+    buf = torch.randn(2 * ci, 2 * co, device="cuda")                   # dW_big^T: [(s, i)][(s, o)]
+    g = torch.full((co, ci), 7.0, device="cuda")
+    t = _table(unpack=True)
+    t.add(buf.data_ptr(), g.data_ptr(), E.PACK_PAIR_LIN, co * ci, 2 * co, co, ci, 0)
+    co3 = ci3 = 32
+    buf3 = torch.randn(27 * 2 * ci3, 2 * co3, device="cuda")           # [(ptap, s_in, i)][(s_out, o)]
+    g3 = torch.full((co3, ci3, 3, 3, 3), 7.0, device="cuda")
+    t.add(buf3.data_ptr(), g3.data_ptr(), E.PACK_PAIR_CONV3, g3.numel(), 2 * co3, co3, ci3, 0)
+    t.run("ctu_unpack_grads")
+    assert torch.allclose(g, (buf[:ci, :co] + buf[ci:, co:]).t())
+    b = buf3.reshape(3, 3, 3, 2, ci3, 2, co3)                          # [tx][ty][pz][s_in][i][s_out][o]
+    ref = torch.zeros_like(g3)
+    for s_out in range(2):
+        for s_in in range(2):
+            for pz in range(3):
+                dz = 2 * (pz - 1) + s_in - s_out
+                if -1 <= dz <= 1:
+                    ref[:, :, :, :, dz + 1] += b[:, :, pz, s_in, :, s_out, :].permute(3, 2, 0, 1)
+    assert torch.allclose(g3, ref, atol=1e-6)
+
+
+def test_x3_relayout_and_stats_fold():
+    """CTU_PACK_X3_FROM_PACKED == ops.x3_layout (the weight copy of the two-plane 3x3x3 kernel); ctu_stats_fold merges the two
+    column halves of paired InstanceNorm sums."""
+    from hybrid_ctunet_b200 import engine as E, ops
+    torch.manual_seed(5)
+    packed = torch.randn(128, 27 * 64, device="cuda").to(BF)
+    dst = torch.full((9 * 2 * 192, 64), 7.0, device="cuda", dtype=BF)
+    t = _table()
+    t.add(packed.data_ptr(), dst.data_ptr(), E.PACK_X3_FROM_PACKED, dst.shape[0], 64, 128, 64, 0)
+    t.run("ctu_pack_weights")
+    assert torch.equal(dst, ops.x3_layout(packed, 64))
+    st = torch.randn(3, 64, 2, device="cuda", dtype=torch.float64)
+    ref = (st[:, :32] + st[:, 32:]) * 0.5
+    ops.stats_fold(st, 32, 0.5)
+    assert torch.equal(st[:, :32], ref) and torch.equal(st[:, 32:], ref)
+    wide = torch.randn(2, 256, 4, device="cuda", dtype=torch.float64)
+    ref = wide[:, :128] + wide[:, 128:]
+    ops.stats_fold(wide, 128, 1.0)
+    assert torch.equal(wide[:, :128], ref) and torch.equal(wide[:, 128:], ref)
