@@ -33,6 +33,7 @@ SIGS = {
     "ctu_cast_f32_bf16": (P, L, P, L, L, I, P),
     "ctu_patchify_ln_bwd": (P, I, I, I, I, I, P, P, P, F, P),
     "ctu_ensemble_argmax": (P, P, I, L, P, P, P, P, P, P),
+    "ctu_cin1_k1_stats": (P, P, I, L, I, P, P, I, P),
     "ctu_cc_filter_largest": (P, P, I, I, I, D, I, D, P, P, P, P),
     "ctu_adamw_step": (P, I, L, D, D, D, D, D, L, P),
     "ctu_pack_weights": (P, I, L, P),

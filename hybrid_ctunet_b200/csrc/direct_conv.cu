@@ -63,9 +63,58 @@ __global__ void __launch_bounds__(128) conv_cin1_kernel(const float* __restrict_
   }
 }
 
+// First and second moment of the single-channel input per batch item: sums over S voxels into mom[b] = (sum x, sum x^2)
+// (fp64 atomics; mom zeroed by the caller).
+__global__ void __launch_bounds__(256) cin1_moments_kernel(const float* __restrict__ x, long long S, double* __restrict__ mom) {
+  __shared__ double red[2][8];
+  const float* xb = x + (long long)blockIdx.y * S;
+  double s1 = 0.0, s2 = 0.0;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < S; v += (long long)gridDim.x * blockDim.x) {
+    const double t = (double)__ldg(xb + v);
+    s1 += t;
+    s2 += t * t;
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[threadIdx.x][k];
+    atomicAdd(mom + 2 * blockIdx.y + threadIdx.x, t);
+  }
+}
+
+// InstanceNorm sums of a 1 -> C pointwise convolution r[v][c] = x[v] * w[c] without reading r: sum r = w_c sum x,
+// sum r^2 = w_c^2 sum x^2.
+__global__ void cin1_k1_stats_kernel(const double* __restrict__ mom, const float* __restrict__ w, int B, int C,
+                                     double* __restrict__ stats, int ld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  const double wc = (double)w[c];
+  stats[((long long)b * ld + c) * 2] = wc * mom[2 * b];
+  stats[((long long)b * ld + c) * 2 + 1] = wc * wc * mom[2 * b + 1];
+}
+
 }  // namespace ctu
 
 using namespace ctu;
+
+extern "C" int ctu_cin1_k1_stats(const float* x, const float* w, int B, long long S, int C, double* mom, double* stats,
+                                 int stats_ld, void* stream) {
+  if (!x || !w || !mom || !stats || B <= 0 || S <= 0 || C <= 0 || stats_ld < C) return CTU_E_BADARG;
+  long long nb = (S + 256 * 16 - 1) / (256 * 16);
+  if (nb > 592) nb = 592;
+  cin1_moments_kernel<<<dim3((unsigned)nb, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(x, S, mom);
+  cin1_k1_stats_kernel<<<(B * C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mom, w, B, C, stats, stats_ld);
+  count_launch(2);
+  return (int)cudaGetLastError();
+}
 
 // x: fp32 [B][X][Y][Z] (the reference's [B,1,X,Y,Z]); w: fp32 [kx*ky*kz][64] (tap-major); out: bf16 channels-last
 // [B][Xo][Yo][Zo][ldo], Xo = (X + 2*px - kx)/sx + 1 etc.

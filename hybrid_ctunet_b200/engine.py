@@ -1246,7 +1246,11 @@ class Engine:
         c2 = self.conv3x3(a1, pre + ".conv2.conv", st2)
         r = self.conv_cin1(x_in, pre + ".conv3.conv", self._empty(B, X, Y, Z, 64), k=(1, 1, 1), s=(1, 1, 1), p=(0, 0, 0))
         st3 = self.stats.take(B, 64)
-        ops.in_stats(r, st3)
+        if _CIN1_TC and x_in.dtype == F32 and x_in.is_contiguous():
+            # the statistics of a pointwise single-channel convolution follow from the moments of its input: no pass over r
+            ops.cin1_k1_stats(x_in, self.w.conv_cin1(pre + ".conv3.conv"), self.stats.take(B, 1), st3)
+        else:
+            ops.in_stats(r, st3)
         return self.in_apply(c2, st2, res=r, rstats=st3, out=out)
 
     def pixelweight_attention(self, pre: str, x1, x2):

@@ -337,6 +337,18 @@ def _bsc(x: torch.Tensor):
     return B, S, C_
 
 
+def cin1_k1_stats(x_in: torch.Tensor, w: torch.Tensor, mom: torch.Tensor, stats: torch.Tensor) -> torch.Tensor:
+    """InstanceNorm sums of r[v][c] = x[v] * w[c] from the moments of x (ctu_cin1_k1_stats).  x_in: fp32 [B, 1, X, Y, Z]
+    contiguous; w: fp32 [C] (or [1, C]); mom: fp64 [B, 1, 2] zeroed; stats: fp64 [B, ld, 2]."""
+    lib = _lib.require_device()
+    B = x_in.shape[0]
+    S = x_in.numel() // B
+    assert x_in.dtype == torch.float32 and x_in.is_contiguous() and w.dtype == torch.float32 and w.is_contiguous()
+    check(lib.ctu_cin1_k1_stats(x_in.data_ptr(), w.data_ptr(), B, S, int(w.numel()), mom.data_ptr(), stats.data_ptr(),
+                                int(stats.shape[-2]), _stream()), "ctu_cin1_k1_stats")
+    return stats
+
+
 def stats_fold(stats: torch.Tensor, half: int, scale: float) -> torch.Tensor:
     """stats: fp64 [B, ld, width] sums of a PAIRED tensor (columns c and c + half are one channel): both halves become
     (v[c] + v[c + half]) * scale (ctu_stats_fold)."""

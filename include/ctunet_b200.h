@@ -346,6 +346,12 @@ int ctu_dice_ce_finalize(const ctu_loss_heads* heads, const double* sums, float*
 int ctu_gather3d(const float* src, float* dst, int B, int X, int Y, int Z, int Xo, int Yo, int Zo, const int* ix,
                  const int* iy, const int* iz, void* stream);
 
+/* InstanceNorm sums of the pointwise single-channel convolution r[v][c] = x[v] * w[c] (vit_encoder0's conv3 + norm3 residual
+ * branch, hybrid_CTUNet.py:75,88-91 with in_channels = 1) WITHOUT a pass over r: stats[b][c] = (w_c sum_v x, w_c^2 sum_v x^2).
+ * x: fp32 [B][S]; w: fp32 [C]; mom: fp64 [B][2] scratch, zeroed by the caller; stats: fp64 [B][stats_ld][2] (written). */
+int ctu_cin1_k1_stats(const float* x, const float* w, int B, long long S, int C, double* mom, double* stats, int stats_ld,
+                      void* stream);
+
 /* Post-processing of a predicted label volume (test_CTUNet_final.py:132-190, remove_all_but_the_largest_connected_component,
  * one class or class group per call): the voxels whose label is in the set `member` (uint8 [256], non-zero = member) are
  * split into connected components (6-connectivity = scipy.ndimage.label's default structure); every component that is not

@@ -222,3 +222,18 @@ def test_blend_bit_exact():
     out = torch.empty_like(acc0)
     ops.blend_normalize(acc0, cnt, out)
     assert torch.equal(out, ref0 / refc)
+
+
+def test_cin1_k1_stats_equal_the_sums_of_the_product():
+    """ctu_cin1_k1_stats: InstanceNorm sums of r[v][c] = x[v] * w[c] (vit_encoder0 conv3 with in_channels = 1,
+    hybrid_CTUNet.py:75,88-91) from the moments of x, against fp64 sums of the product itself."""
+    from hybrid_ctunet_b200 import ops
+    torch.manual_seed(4)
+    x = torch.rand(3, 1, 20, 18, 22, device="cuda") * 2 - 0.5
+    w = torch.randn(64, device="cuda")
+    mom = torch.zeros(3, 1, 2, device="cuda", dtype=torch.float64)
+    st = torch.full((3, 64, 2), 7.0, device="cuda", dtype=torch.float64)
+    ops.cin1_k1_stats(x, w, mom, st)
+    r = x.double().reshape(3, -1, 1) * w.double()
+    assert torch.allclose(st[..., 0], r.sum(1), rtol=1e-10, atol=1e-8)
+    assert torch.allclose(st[..., 1], (r * r).sum(1), rtol=1e-10, atol=1e-8)
