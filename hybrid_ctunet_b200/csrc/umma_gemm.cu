@@ -570,9 +570,11 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, CTAS_PER_SM) umma_gemm_ke
 #pragma unroll
             for (int sl = 0; sl < SLABS; ++sl) {
               if (n0 + sl * 64 < p.n_real) {
+                // (u = 1, a = 0, colbase = n0 for everything but the up-sampling GEMMs)
                 asm volatile(
                     "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(&tmC),
-                    "r"(smem_u32(cbuf + sl * SLAB_BYTES)), "r"(n0 + sl * 64), "r"(tc.x1), "r"(tc.x2), "r"(tc.x3), "r"(tc.t4)
+                    "r"(smem_u32(cbuf + sl * SLAB_BYTES)), "r"(colbase + sl * 64), "r"(tc.x1 * p.u1 + a1), "r"(tc.x2 * p.u2 + a2),
+                    "r"(tc.x3 * p.u3 + a3), "r"(tc.t4)
                     : "memory");
               }
             }
@@ -751,16 +753,24 @@ extern "C" int ctu_umma_gemm(const ctu_gemm_desc* d, void* stream_) {
     if (r != CUDA_SUCCESS) return CTU_E_DRIVER;
   }
   // C: bf16 row outputs of plain GEMMs / convs go through a swizzled smem tile and TMA stores
-  const bool tma_store = d->out_mode == CTU_OUT_BF16_ROWS && d->convt_cout == 0 && d->block_n >= 64;
+  // (transposed convolution / pixel shuffle: the tile's voxels land on a stride-u lattice of the up-sampled output — the
+  // same TMA store with ELEMENT STRIDES u along the spatial axes and the sub-voxel offset in the start coordinates)
+  static const int convt_tma = [] { const char* e = getenv("CTU_CONVT_TMA_STORE"); return e ? atoi(e) : 1; }();
+  const bool convt = d->convt_cout > 0;
+  const bool tma_store = d->out_mode == CTU_OUT_BF16_ROWS && d->block_n >= 64 &&
+                         (!convt || (convt_tma && d->convt_cout % 64 == 0 && d->u1 <= 8 && d->u2 <= 8 && d->u3 <= 8 &&
+                                     d->b1 * d->u1 <= 256 && d->b2 * d->u2 <= 256 && d->b3 * d->u3 <= 256));
   if (tma_store) {
-    cuuint64_t dims[5] = {(cuuint64_t)d->n_real, (cuuint64_t)d->d1, (cuuint64_t)d->d2, (cuuint64_t)d->d3, (cuuint64_t)d->d4};
+    const int u1 = convt ? d->u1 : 1, u2 = convt ? d->u2 : 1, u3 = convt ? d->u3 : 1;
+    cuuint64_t dims[5] = {(cuuint64_t)(convt ? d->convt_cout : d->n_real), (cuuint64_t)d->d1 * u1, (cuuint64_t)d->d2 * u2,
+                          (cuuint64_t)d->d3 * u3, (cuuint64_t)d->d4};
     cuuint64_t strides[4];
     strides[0] = (cuuint64_t)d->ldc * 2;
-    strides[1] = strides[0] * d->d1;
-    strides[2] = strides[1] * d->d2;
-    strides[3] = strides[2] * d->d3;
-    cuuint32_t box[5] = {64, (cuuint32_t)d->b1, (cuuint32_t)d->b2, (cuuint32_t)d->b3, 1};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    strides[1] = strides[0] * dims[1];
+    strides[2] = strides[1] * dims[2];
+    strides[3] = strides[2] * dims[3];
+    cuuint32_t box[5] = {64, (cuuint32_t)(d->b1 * u1), (cuuint32_t)(d->b2 * u2), (cuuint32_t)(d->b3 * u3), 1};
+    cuuint32_t es[5] = {1, (cuuint32_t)u1, (cuuint32_t)u2, (cuuint32_t)u3, 1};
     void* base = reinterpret_cast<__nv_bfloat16*>(d->out) + d->out_col0;
     CUresult r = tma_encoder()(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p,
