@@ -35,6 +35,8 @@ SIGS = {
     "ctu_ensemble_argmax": (P, P, I, L, P, P, P, P, P, P),
     "ctu_cin1_k1_stats": (P, P, I, L, I, P, P, I, P),
     "ctu_cc_filter_largest": (P, P, I, I, I, D, I, D, P, P, P, P),
+    "ctu_invert_resample": (P, I, P, P, P),
+    "ctu_invert_ensemble_argmax": (P, P, I, P, P, P, P, P, P, P),
     "ctu_adamw_step": (P, I, L, D, D, D, D, D, L, P),
     "ctu_pack_weights": (P, I, L, P),
     "ctu_unpack_grads": (P, I, L, P),

@@ -63,6 +63,15 @@ class LossHeads(C.Structure):
     ]
 
 
+class InvertGeom(C.Structure):
+    """ctu_invert_geom of include/ctunet_b200.h (field for field)."""
+    _fields_ = [
+        ("m", C.c_double * 12),
+        ("out_size", C.c_int32 * 3), ("pad_size", C.c_int32 * 3), ("crop_start", C.c_int32 * 3), ("pred_size", C.c_int32 * 3),
+        ("mode", C.c_int32),
+    ]
+
+
 def lib_path() -> str:
     return _build.LIB_PATH
 

@@ -361,6 +361,32 @@ int ctu_cin1_k1_stats(const float* x, const float* w, int B, long long S, int C,
 int ctu_cc_filter_largest(uint8_t* image, const uint8_t* member, int X, int Y, int Z, double volume_per_voxel, int has_min,
                           double min_valid, int* parent, int* sizes, int* summary, void* stream);
 
+/* `Invertd` of the evaluation scripts (test_CTUNet.py:162-199; test_CTUNet_final.py:470-505; the inverse chain of
+ * utils/data_utils.py:103-116: CropForegroundd -> zero pad, Spacingd -> trilinear resample with border padding and
+ * align_corners=False computed in float64, Orientationd -> flips / transposes) folded into one index map:
+ *   m         row-major 3x4, (o0, o1, o2, 1) of the OUTPUT grid (the file's own voxel grid) -> fractional voxel index in
+ *             the padded grid (the grid before CropForegroundd); coordinates clamp to [0, pad_size - 1]
+ *   out_size  spatial shape of the output; pad_size: shape before CropForegroundd
+ *   crop_start / pred_size  where pred[.., 0, 0, 0] sits in the padded grid and pred's spatial shape: corners outside
+ *             [crop_start, crop_start + pred_size) read 0 (the pad)
+ *   mode      0 = nearest (round half to even), 1 = trilinear (`nearest_interp=False`, what the scripts use). */
+typedef struct ctu_invert_geom {
+  double m[12];
+  int32_t out_size[3];
+  int32_t pad_size[3];
+  int32_t crop_start[3];
+  int32_t pred_size[3];
+  int32_t mode;
+} ctu_invert_geom;
+
+/* out[c][o] = resample(pred[c]) : pred fp32 [C][pred_size], out fp32 [C][out_size] — the tensor Invertd returns. */
+int ctu_invert_resample(const float* pred, int C, const ctu_invert_geom* geom, float* out, void* stream);
+
+/* Invertd of both models' logits fused with ctu_ensemble_argmax (same outputs, over out_size voxels; labels / counts on the
+ * output grid): the two inverted [C][out_size] fp32 volumes are never written.  C = 14. */
+int ctu_invert_ensemble_argmax(const float* p1, const float* p2, int C, const ctu_invert_geom* geom, uint8_t* mask,
+                               uint8_t* mask1, uint8_t* mask2, const float* labels, unsigned long long* counts, void* stream);
+
 /* Multi-tensor AdamW: the optimizer step of main_CTUNet.py:190-193 (torch.optim.AdamW(lr, weight_decay), no amsgrad) as
  * ONE launch over a device-resident item table — one item per parameter that has a gradient; all four tensors fp32 and
  * contiguous, numel elements each; unit0 = index of the item's first work unit (1024 elements per unit), items sorted by

@@ -19,7 +19,8 @@ def test_header_declares_the_hot_path_entry_points():
                  "ctu_umma_wgrad", "ctu_in_bwd_stats", "ctu_in_bwd_apply", "ctu_layernorm_bwd", "ctu_attention_bwd",
                  "ctu_pwa_fuse_bwd", "ctu_gelu_bwd", "ctu_colsum", "ctu_accumulate", "ctu_pack_weights", "ctu_unpack_grads",
                  "ctu_dice_ce_fwd", "ctu_dice_ce_bwd", "ctu_ensemble_argmax", "ctu_adamw_step",
-                 "ctu_set_persistent_sm_limit", "ctu_ffn_fused", "ctu_dice_ce_finalize", "ctu_gather3d", "ctu_cc_filter_largest", "ctu_stats_fold"):
+                 "ctu_set_persistent_sm_limit", "ctu_ffn_fused", "ctu_dice_ce_finalize", "ctu_gather3d", "ctu_cc_filter_largest", "ctu_stats_fold",
+                 "ctu_invert_resample", "ctu_invert_ensemble_argmax"):
         assert must in names
 
 
@@ -58,6 +59,16 @@ def test_wgrad_struct_matches_header_field_order():
         if m and "{" not in decl:
             fields += [f.strip().lstrip("*") for f in m.group(3).split(",") if f.strip()]
     assert fields == [f[0] for f in WgradDesc._fields_]
+
+
+def test_invert_geom_struct_matches_header_field_order():
+    from hybrid_ctunet_b200.lib import InvertGeom
+    src = open(os.path.join(ROOT, "include", "ctunet_b200.h")).read()
+    start = src.index("typedef struct ctu_invert_geom {") + len("typedef struct ctu_invert_geom {")
+    body = src[start:src.index("} ctu_invert_geom;")]
+    fields = re.findall(r"(?:double|int32_t)\s+(\w+)(?:\[\d+\])?;", body)
+    assert fields == [f[0] for f in InvertGeom._fields_]
+    assert ctypes.sizeof(InvertGeom) == 12 * 8 + 13 * 4 + 4   # 148 bytes + tail padding to the 8-byte alignment
 
 
 def test_product_package_never_imports_the_oracle():
