@@ -17,7 +17,7 @@
 namespace ctu {
 
 struct InvertSample {
-  long long off[8];   // offset of each corner inside one class plane of the cropped prediction
+  long long base;     // offset of corner 0 inside one class plane of the cropped prediction (may lie outside: see valid)
   double w[8];        // grid_sample's weight of the corner
   unsigned valid;     // bit k: corner k lies inside the padded grid AND inside the crop (otherwise it contributes 0)
 };
@@ -49,7 +49,7 @@ __device__ __forceinline__ void invert_sample(const InvertGeomDev& g, int o0, in
       ok = ok && i >= 0 && i < g.pad[a] && p >= 0 && p < g.pred[a];
       off = off * g.pred[a] + p;
     }
-    s.off[0] = ok ? off : 0;
+    s.base = ok ? off : 0;
     s.w[0] = 1.0;
     s.valid = ok ? 1u : 0u;
     return;
@@ -72,34 +72,43 @@ __device__ __forceinline__ void invert_sample(const InvertGeomDev& g, int o0, in
     const int px = ix - g.crop[0], py = iy - g.crop[1], pz = iz - g.crop[2];
     const bool ok = ix < g.pad[0] && iy < g.pad[1] && iz < g.pad[2] &&          // within_bounds_3d (lower corners are >= 0)
                     px >= 0 && px < g.pred[0] && py >= 0 && py < g.pred[1] && pz >= 0 && pz < g.pred[2];
-    s.off[k] = ok ? ((long long)px * g.pred[1] + py) * g.pred[2] + pz : 0;
     s.valid |= ok ? (1u << k) : 0u;
   }
+  s.base = ((long long)(i0[0] - g.crop[0]) * g.pred[1] + (i0[1] - g.crop[1])) * g.pred[2] + (i0[2] - g.crop[2]);
 }
 
-__device__ __forceinline__ float invert_value(const float* __restrict__ plane, const InvertSample& s, int mode) {
-  if (mode == 0) return (s.valid & 1u) ? __ldg(plane + s.off[0]) : 0.f;
+// sx, sy: element strides of the x / y axes of the prediction (z is contiguous)
+__device__ __forceinline__ float invert_value(const float* __restrict__ plane, const InvertSample& s, int mode, int sx, int sy) {
+  const float* p = plane + s.base;
+  if (mode == 0) return (s.valid & 1u) ? __ldg(p) : 0.f;
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)   // all eight loads in flight before the dependent float64 chain
+    v[k] = (s.valid & (1u << k)) ? __ldg(p + ((k >> 2) & 1) * sx + ((k >> 1) & 1) * sy + (k & 1)) : 0.f;
   double acc = 0.0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k)
-    if (s.valid & (1u << k)) acc = __dadd_rn(acc, __dmul_rn((double)__ldg(plane + s.off[k]), s.w[k]));   // no FMA: the host kernel has none
+  for (int k = 0; k < 8; ++k)   // a corner that is out of bounds adds nothing in grid_sample; here it adds +0.0 * w
+    acc = __dadd_rn(acc, __dmul_rn((double)v[k], s.w[k]));   // no FMA: the host kernel has none
   return (float)acc;
 }
 
-__global__ void __launch_bounds__(256) invert_resample_kernel(const float* __restrict__ pred, int C, InvertGeomDev g,
+__global__ void __launch_bounds__(256, 4) invert_resample_kernel(const float* __restrict__ pred, int C, InvertGeomDev g,
                                                               float* __restrict__ out) {
-  const long long V = (long long)g.out[0] * g.out[1] * g.out[2];
+  const unsigned V = (unsigned)g.out[0] * g.out[1] * g.out[2];   // < 2^31: checked by the caller
   const long long P = (long long)g.pred[0] * g.pred[1] * g.pred[2];
-  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
-    const int o2 = (int)(v % g.out[2]), o1 = (int)((v / g.out[2]) % g.out[1]), o0 = (int)(v / ((long long)g.out[2] * g.out[1]));
+  const int sy = g.pred[2], sx = g.pred[1] * g.pred[2];
+  for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+    const unsigned q = v / (unsigned)g.out[2];
+    const int o2 = (int)(v - q * g.out[2]), o0 = (int)(q / (unsigned)g.out[1]), o1 = (int)(q - (unsigned)o0 * g.out[1]);
     InvertSample s;
     invert_sample(g, o0, o1, o2, s);
-    for (int c = 0; c < C; ++c) out[(long long)c * V + v] = invert_value(pred + (long long)c * P, s, g.mode);
+#pragma unroll 2
+    for (int c = 0; c < C; ++c) out[(long long)c * V + v] = invert_value(pred + (long long)c * P, s, g.mode, sx, sy);
   }
 }
 
 template <int C>
-__global__ void __launch_bounds__(256) invert_ensemble_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+__global__ void __launch_bounds__(256, 3) invert_ensemble_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                                                               InvertGeomDev g, uint8_t* __restrict__ mask,
                                                               uint8_t* __restrict__ mask1, uint8_t* __restrict__ mask2,
                                                               const float* __restrict__ labels,
@@ -107,10 +116,12 @@ __global__ void __launch_bounds__(256) invert_ensemble_kernel(const float* __res
   __shared__ unsigned int sc[3 * C * 3];
   for (int i = threadIdx.x; i < 3 * C * 3; i += 256) sc[i] = 0;
   __syncthreads();
-  const long long V = (long long)g.out[0] * g.out[1] * g.out[2];
+  const unsigned V = (unsigned)g.out[0] * g.out[1] * g.out[2];
   const long long P = (long long)g.pred[0] * g.pred[1] * g.pred[2];
-  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
-    const int o2 = (int)(v % g.out[2]), o1 = (int)((v / g.out[2]) % g.out[1]), o0 = (int)(v / ((long long)g.out[2] * g.out[1]));
+  const int sy = g.pred[2], sx = g.pred[1] * g.pred[2];
+  for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+    const unsigned q = v / (unsigned)g.out[2];
+    const int o2 = (int)(v - q * g.out[2]), o0 = (int)(q / (unsigned)g.out[1]), o1 = (int)(q - (unsigned)o0 * g.out[1]);
     InvertSample s;
     invert_sample(g, o0, o1, o2, s);
     // from here on: ensemble_kernel (ensemble.cu) on the interpolated scores, statement for statement
@@ -119,8 +130,8 @@ __global__ void __launch_bounds__(256) invert_ensemble_kernel(const float* __res
     int ia = 0, ib = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      a[c] = invert_value(p1 + (long long)c * P, s, g.mode);
-      b[c] = invert_value(p2 + (long long)c * P, s, g.mode);
+      a[c] = invert_value(p1 + (long long)c * P, s, g.mode, sx, sy);
+      b[c] = invert_value(p2 + (long long)c * P, s, g.mode, sx, sy);
       if (a[c] > ma) { ma = a[c]; ia = c; }
       if (b[c] > mb) { mb = b[c]; ib = c; }
     }
@@ -170,6 +181,8 @@ static int invert_geom(const ctu_invert_geom* g, InvertGeomDev& d) {
   }
   d.mode = g->mode;
   if (d.mode != 0 && d.mode != 1) return CTU_E_UNSUPPORTED;
+  if ((long long)d.out[0] * d.out[1] * d.out[2] > 0x7fffffffLL || (long long)d.pred[0] * d.pred[1] * d.pred[2] > 0x7fffffffLL)
+    return CTU_E_UNSUPPORTED;   // 32-bit voxel indices inside one class plane
   return 0;
 }
 
@@ -190,7 +203,7 @@ extern "C" int ctu_invert_resample(const float* pred, int C, const ctu_invert_ge
   if (rc != 0) return rc;
   if (!pred || !out || C <= 0) return CTU_E_BADARG;
   const long long V = (long long)g.out[0] * g.out[1] * g.out[2];
-  invert_resample_kernel<<<invert_grid(V, 8), 256, 0, (cudaStream_t)stream>>>(pred, C, g, out);
+  invert_resample_kernel<<<invert_grid(V, 16), 256, 0, (cudaStream_t)stream>>>(pred, C, g, out);
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -205,7 +218,7 @@ extern "C" int ctu_invert_ensemble_argmax(const float* p1, const float* p2, int 
   if (!p1 || !p2 || (!mask && !mask1 && !mask2 && !counts)) return CTU_E_BADARG;
   if (C != 14) return CTU_E_UNSUPPORTED;
   const long long V = (long long)g.out[0] * g.out[1] * g.out[2];
-  invert_ensemble_kernel<14><<<invert_grid(V, 8), 256, 0, (cudaStream_t)stream>>>(p1, p2, g, mask, mask1, mask2, labels, counts);
+  invert_ensemble_kernel<14><<<invert_grid(V, 12), 256, 0, (cudaStream_t)stream>>>(p1, p2, g, mask, mask1, mask2, labels, counts);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -41,10 +41,12 @@ def ensemble_masks(pred1: torch.Tensor, pred2: torch.Tensor, labels: Optional[to
 
 
 def hybrid_ctunet_inference(inputs: torch.Tensor, ctunet, tunet, roi_size=(96, 96, 96), sw_batch_size: int = 4,
-                            labels: Optional[torch.Tensor] = None, shard_group=None) -> Dict[str, torch.Tensor]:
+                            labels: Optional[torch.Tensor] = None, shard_group=None, invert=None) -> Dict[str, torch.Tensor]:
     """The "Hybrid-CTUNet" configuration of test_CTUNet_final.py:539-552 for one volume [1, 1, X, Y, Z]: CTUNet's
     ResNet-branch head blended at overlap 0.5, an independently trained TUNet's first head blended at overlap 0.7
-    (one-head sliding window), then the mask-complementation ensemble.  Windows are sharded over `shard_group`."""
+    (one-head sliding window), then the mask-complementation ensemble.  Windows are sharded over `shard_group`.
+    `invert` (an `invert.InvertGeometry`): the scripts' `Invertd` step between the two (test_CTUNet_final.py:541-545) — the
+    masks (and `labels`) are then on the voxel grid of the file, computed by the fused inverse + ensemble kernel."""
     from .sliding_window import sliding_window_inference_one_head
     with torch.no_grad():
         # only CTUNet's ResNet-branch head is used (`[0]` of the two blended heads in the reference script): blend just
@@ -53,4 +55,7 @@ def hybrid_ctunet_inference(inputs: torch.Tensor, ctunet, tunet, roi_size=(96, 9
                                                mode="gaussian", shard_group=shard_group)
         p2 = sliding_window_inference_one_head(inputs, roi_size, sw_batch_size, tunet, overlap=0.7, mode="gaussian",
                                                shard_group=shard_group)
+        if invert is not None:
+            from .invert import invert_ensemble_masks
+            return invert_ensemble_masks(p1[0], p2[0], invert, labels)
         return ensemble_masks(p1[0], p2[0], labels)

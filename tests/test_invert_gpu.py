@@ -125,3 +125,29 @@ def test_full_size_properties():
     two = ensemble_masks(i1, i2, labels)
     for k in ("ensemble", "head1", "head2", "counts"):
         assert torch.equal(fused[k], two[k]), k
+
+
+def test_hybrid_pipeline_with_invert_step():
+    """hybrid_ctunet_inference(..., invert=geometry) = sliding windows of both models -> Invertd -> ensemble
+    (test_CTUNet_final.py:539-552), here with stand-in predictors so that only the plumbing is under test."""
+    from hybrid_ctunet_b200.ensemble import ensemble_masks, hybrid_ctunet_inference
+    from hybrid_ctunet_b200.invert import invert_pred
+    from hybrid_ctunet_b200.sliding_window import sliding_window_inference_one_head
+    from test_invert_cpu import _geom
+    from oracle import invert_oracle as IO
+    img, aff = IO.make_case(shape=(70, 64, 30), spacing_mm=(0.8, 0.8, 3.0), axcodes="LAS", seed=4)
+    trace = IO.forward_trace(img, aff, (1.5, 1.5, 2.0))
+    g = _geom(trace)
+    vol = torch.from_numpy(trace["image"]).cuda()[None]                        # [1, 1, x, y, z] as the loader yields it
+    scale = torch.linspace(0.5, 2.0, 14, device="cuda").view(1, 14, 1, 1, 1)
+    ctunet = lambda w: ((torch.sin(7.0 * w * scale),), (torch.zeros_like(w).repeat(1, 14, 1, 1, 1),))
+    tunet = lambda w: (torch.cos(5.0 * w * scale),)
+    roi = (32, 32, 32)
+    lab = torch.randint(0, 14, img.shape[1:], device="cuda").float()
+    got = hybrid_ctunet_inference(vol, ctunet, tunet, roi_size=roi, labels=lab, invert=g)
+    p1 = sliding_window_inference_one_head(vol, roi, 4, lambda w: (ctunet(w)[0][0],), overlap=0.5, mode="gaussian")[0]
+    p2 = sliding_window_inference_one_head(vol, roi, 4, tunet, overlap=0.7, mode="gaussian")[0]
+    ref = ensemble_masks(invert_pred(p1, g), invert_pred(p2, g), lab)
+    assert got["ensemble"].shape == img.shape[1:]
+    for k in ("ensemble", "head1", "head2", "counts"):
+        assert torch.equal(got[k], ref[k]), k
