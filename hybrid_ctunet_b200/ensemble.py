@@ -59,3 +59,39 @@ def hybrid_ctunet_inference(inputs: torch.Tensor, ctunet, tunet, roi_size=(96, 9
             from .invert import invert_ensemble_masks
             return invert_ensemble_masks(p1[0], p2[0], invert, labels)
         return ensemble_masks(p1[0], p2[0], labels)
+
+
+def evaluate_cases(cases, ctunet, tunet, roi_size=(96, 96, 96), sw_batch_size: int = 4, postprocess: bool = True,
+                   dice_threshold: float = 0.0, advanced_postprocessing: bool = True, shard_group=None) -> Dict[str, object]:
+    """The evaluation loop of test_CTUNet_final.py:527-655 with every per-voxel step on the device.  `cases`: an iterable of
+    dicts with "image" [1, 1, x, y, z] (the loader's resampled, cropped tensor), "label" (the file's own label volume
+    [X0, Y0, Z0], any leading 1s), "geometry" (an `invert.InvertGeometry`, or None when the image already is on the label's
+    grid) and "volume_per_voxel" (float, for the size thresholds).  Per case: both sliding windows, `Invertd` + softmax
+    average + three argmax masks + 13-class Dice in one kernel; then, over all cases, `determine_postprocessing`
+    (largest-connected-component rule) as the script's closing step.  Returns the per-case masks (uint8, CUDA), the three
+    Dice tables [case][13] (ResNet head / TUNet head / ensemble, the script's `dice_list_case_res / _vit / dice_list_case`),
+    their organ means and — with `postprocess` — the post-processed masks and their mean Dice (`com_dice`)."""
+    import numpy as np
+    from .postprocess import com_dice, determine_postprocessing
+    masks, labels, vpv = [], [], []
+    tables = {"res": [], "vit": [], "ensemble": []}
+    for case in cases:
+        lab = case["label"]
+        lab = lab.reshape(lab.shape[-3:])
+        out = hybrid_ctunet_inference(case["image"], ctunet, tunet, roi_size, sw_batch_size, labels=lab,
+                                      shard_group=shard_group, invert=case.get("geometry"))
+        dice = out["dice"][:, 1:].cpu().numpy()           # rows: ensemble, head 1 (ResNet branch), head 2 (TUNet); organs 1..13
+        tables["ensemble"].append(dice[0])
+        tables["res"].append(dice[1])
+        tables["vit"].append(dice[2])
+        masks.append(out["ensemble"])
+        labels.append(lab)
+        vpv.append(float(case.get("volume_per_voxel", 1.0)))
+    res: Dict[str, object] = {"masks": masks, "dice": {k: np.asarray(v) for k, v in tables.items()},
+                              "mean_organ_dice": {k: np.mean(np.asarray(v), axis=0) for k, v in tables.items()}}
+    if postprocess and masks:
+        post = determine_postprocessing(masks, labels, vpv, dice_threshold=dice_threshold,
+                                        advanced_postprocessing=advanced_postprocessing)
+        res["masks_postprocessed"] = post
+        res["mean_organ_dice_postprocessed"] = np.asarray(com_dice(post, labels))
+    return res

@@ -151,3 +151,36 @@ def test_hybrid_pipeline_with_invert_step():
     assert got["ensemble"].shape == img.shape[1:]
     for k in ("ensemble", "head1", "head2", "counts"):
         assert torch.equal(got[k], ref[k]), k
+
+
+def test_evaluate_cases_runs_the_scripts_closing_loop():
+    """evaluate_cases = per case: sliding windows -> Invertd + ensemble + Dice; over the cases: determine_postprocessing
+    (test_CTUNet_final.py:527-655).  Stand-in predictors; checked against the pieces called by hand and against the
+    reference's Dice definition evaluated on the host."""
+    from hybrid_ctunet_b200.ensemble import evaluate_cases, hybrid_ctunet_inference
+    from hybrid_ctunet_b200.postprocess import com_dice, determine_postprocessing
+    from test_invert_cpu import _geom
+    from oracle import invert_oracle as IO
+    scale = torch.linspace(0.5, 2.0, 14, device="cuda").view(1, 14, 1, 1, 1)
+    ctunet = lambda w: ((torch.sin(9.0 * w * scale),), (torch.zeros_like(w).repeat(1, 14, 1, 1, 1),))
+    tunet = lambda w: (torch.cos(4.0 * w * scale),)
+    cases = []
+    for seed, ax in ((1, "LAS"), (2, "RAS")):
+        img, aff = IO.make_case(shape=(60, 56, 28), spacing_mm=(0.8, 0.8, 3.0), axcodes=ax, seed=seed)
+        trace = IO.forward_trace(img, aff, (1.5, 1.5, 2.0))
+        lab = torch.from_numpy(np.random.default_rng(seed).integers(0, 14, img.shape[1:])).cuda().float()
+        cases.append({"image": torch.from_numpy(trace["image"]).cuda()[None], "label": lab[None, None], "geometry": _geom(trace),
+                      "volume_per_voxel": 0.8 * 0.8 * 3.0})
+    res = evaluate_cases(cases, ctunet, tunet, roi_size=(32, 32, 32))
+    assert res["dice"]["ensemble"].shape == (2, 13) and len(res["masks"]) == 2
+    for i, case in enumerate(cases):
+        one = hybrid_ctunet_inference(case["image"], ctunet, tunet, (32, 32, 32), labels=case["label"][0, 0], invert=case["geometry"])
+        assert torch.equal(one["ensemble"], res["masks"][i])
+        m, l = one["ensemble"].cpu().numpy(), case["label"][0, 0].cpu().numpy()
+        host = [2 * np.sum((m == j) * (l == j)) / (np.sum(m == j) + np.sum(l == j)) if np.sum(l == j) else 0.0 for j in range(1, 14)]
+        assert np.allclose(res["dice"]["ensemble"][i], host, atol=1e-12)
+    labels = [c["label"][0, 0] for c in cases]
+    post = determine_postprocessing(res["masks"], labels, [c["volume_per_voxel"] for c in cases], advanced_postprocessing=True)
+    for a, b in zip(post, res["masks_postprocessed"]):
+        assert torch.equal(torch.as_tensor(a), torch.as_tensor(b))
+    assert np.allclose(res["mean_organ_dice_postprocessed"], com_dice(post, labels))
