@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(256) ensemble_kernel(const float* __restrict__
     int ie = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const float m = (a[c] * ra + b[c] * rb) / 2.0f;
+      // each probability rounded on its own, then the sum (the reference adds two softmax tensors): no FMA contraction
+      const float m = __fadd_rn(__fmul_rn(a[c], ra), __fmul_rn(b[c], rb)) / 2.0f;
       if (m > best) { best = m; ie = c; }
     }
     if (mask) mask[v] = (uint8_t)ie;

@@ -92,6 +92,18 @@ __device__ __forceinline__ float invert_value(const float* __restrict__ plane, c
   return (float)acc;
 }
 
+// the common case: trilinear, all eight corners inside the crop — four row pointers, immediate offsets, no predicates
+__device__ __forceinline__ float invert_value_full(const float* __restrict__ p, const double (&w)[8], int sx, int sy) {
+  const float* q = p + sy;
+  const float* r = p + sx;
+  const float* t = r + sy;
+  const float v[8] = {__ldg(p), __ldg(p + 1), __ldg(q), __ldg(q + 1), __ldg(r), __ldg(r + 1), __ldg(t), __ldg(t + 1)};
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc = __dadd_rn(acc, __dmul_rn((double)v[k], w[k]));
+  return (float)acc;
+}
+
 __global__ void __launch_bounds__(256, 4) invert_resample_kernel(const float* __restrict__ pred, int C, InvertGeomDev g,
                                                               float* __restrict__ out) {
   const unsigned V = (unsigned)g.out[0] * g.out[1] * g.out[2];   // < 2^31: checked by the caller
@@ -102,37 +114,64 @@ __global__ void __launch_bounds__(256, 4) invert_resample_kernel(const float* __
     const int o2 = (int)(v - q * g.out[2]), o0 = (int)(q / (unsigned)g.out[1]), o1 = (int)(q - (unsigned)o0 * g.out[1]);
     InvertSample s;
     invert_sample(g, o0, o1, o2, s);
+    float* o = out + v;
+    if (g.mode == 1 && s.valid == 0xffu) {
+      const float* p = pred + s.base;
 #pragma unroll 2
-    for (int c = 0; c < C; ++c) out[(long long)c * V + v] = invert_value(pred + (long long)c * P, s, g.mode, sx, sy);
+      for (int c = 0; c < C; ++c, p += P, o += V) *o = invert_value_full(p, s.w, sx, sy);
+    } else {
+      for (int c = 0; c < C; ++c, o += V) *o = invert_value(pred + (long long)c * P, s, g.mode, sx, sy);
+    }
   }
 }
 
+// One thread per output voxel.  The gather loop is the resample kernel's (two classes in flight, low register pressure) and
+// parks the interpolated scores of both models in the thread's own shared-memory column; the softmax / mean / argmax stage
+// then pulls them into registers — by then the sample's weights are dead.  From there on it is ensemble_kernel (ensemble.cu)
+// statement for statement.
 template <int C>
-__global__ void __launch_bounds__(256, 3) invert_ensemble_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
+__global__ void __launch_bounds__(256, 4) invert_ensemble_kernel(const float* __restrict__ p1, const float* __restrict__ p2,
                                                               InvertGeomDev g, uint8_t* __restrict__ mask,
                                                               uint8_t* __restrict__ mask1, uint8_t* __restrict__ mask2,
                                                               const float* __restrict__ labels,
                                                               unsigned long long* __restrict__ counts) {
   __shared__ unsigned int sc[3 * C * 3];
+  __shared__ float park[2][C][256];
   for (int i = threadIdx.x; i < 3 * C * 3; i += 256) sc[i] = 0;
   __syncthreads();
   const unsigned V = (unsigned)g.out[0] * g.out[1] * g.out[2];
   const long long P = (long long)g.pred[0] * g.pred[1] * g.pred[2];
   const int sy = g.pred[2], sx = g.pred[1] * g.pred[2];
+  const int tid = threadIdx.x;
   for (unsigned v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
     const unsigned q = v / (unsigned)g.out[2];
     const int o2 = (int)(v - q * g.out[2]), o0 = (int)(q / (unsigned)g.out[1]), o1 = (int)(q - (unsigned)o0 * g.out[1]);
-    InvertSample s;
-    invert_sample(g, o0, o1, o2, s);
-    // from here on: ensemble_kernel (ensemble.cu) on the interpolated scores, statement for statement
+    {
+      InvertSample s;
+      invert_sample(g, o0, o1, o2, s);
+      if (g.mode == 1 && s.valid == 0xffu) {
+        const float* pa = p1 + s.base;
+        const float* pb = p2 + s.base;
+#pragma unroll 2
+        for (int c = 0; c < C; ++c, pa += P, pb += P) {
+          park[0][c][tid] = invert_value_full(pa, s.w, sx, sy);
+          park[1][c][tid] = invert_value_full(pb, s.w, sx, sy);
+        }
+      } else {
+        for (int c = 0; c < C; ++c) {
+          park[0][c][tid] = invert_value(p1 + (long long)c * P, s, g.mode, sx, sy);
+          park[1][c][tid] = invert_value(p2 + (long long)c * P, s, g.mode, sx, sy);
+        }
+      }
+    }
     float a[C], b[C];
     float ma = -INFINITY, mb = -INFINITY;
     int ia = 0, ib = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      a[c] = invert_value(p1 + (long long)c * P, s, g.mode, sx, sy);
-      b[c] = invert_value(p2 + (long long)c * P, s, g.mode, sx, sy);
-      if (a[c] > ma) { ma = a[c]; ia = c; }
+      a[c] = park[0][c][tid];
+      b[c] = park[1][c][tid];
+      if (a[c] > ma) { ma = a[c]; ia = c; }   // first maximal index, like torch.argmax
       if (b[c] > mb) { mb = b[c]; ib = c; }
     }
     float sa = 0.f, sb = 0.f;
@@ -143,7 +182,7 @@ __global__ void __launch_bounds__(256, 3) invert_ensemble_kernel(const float* __
     int ie = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const float m = (a[c] * ra + b[c] * rb) / 2.0f;
+      const float m = __fadd_rn(__fmul_rn(a[c], ra), __fmul_rn(b[c], rb)) / 2.0f;
       if (m > best) { best = m; ie = c; }
     }
     if (mask) mask[v] = (uint8_t)ie;
@@ -218,7 +257,7 @@ extern "C" int ctu_invert_ensemble_argmax(const float* p1, const float* p2, int 
   if (!p1 || !p2 || (!mask && !mask1 && !mask2 && !counts)) return CTU_E_BADARG;
   if (C != 14) return CTU_E_UNSUPPORTED;
   const long long V = (long long)g.out[0] * g.out[1] * g.out[2];
-  invert_ensemble_kernel<14><<<invert_grid(V, 12), 256, 0, (cudaStream_t)stream>>>(p1, p2, g, mask, mask1, mask2, labels, counts);
+  invert_ensemble_kernel<14><<<invert_grid(V, 16), 256, 0, (cudaStream_t)stream>>>(p1, p2, g, mask, mask1, mask2, labels, counts);
   count_launch();
   return (int)cudaGetLastError();
 }
