@@ -359,9 +359,11 @@ def test_fused_dice_ce_matches_oracle(shape):
 
 
 @pytest.mark.parametrize("C,shape,ld_extra,acc", [(64, (2, 8, 12, 16), 0, False), (64, (1, 5, 7, 9), 64, True),
+                                                  (64, (1, 4, 8, 16), 64, True), (64, (2, 16, 16, 24), 0, True),
                                                   (128, (1, 6, 6, 12), 0, True), (256, (2, 3, 4, 5), 0, False)])
 def test_head_backward_fused(C, shape, ld_extra, acc):
-    """ctu_head_bwd (input, weight and bias gradient of a C -> 14 logits head in one pass) vs torch autograd of
+    """ctu_head_bwd (input, weight and bias gradient of a C -> 14 logits head in one pass; C = 64 with a voxel count that is
+    a multiple of 16 runs the tensor-core kernel, the rest the CUDA-core one) vs torch autograd of
     F.conv3d(k=1) + bias on the same bf16-rounded activations; `ld_extra`: the activation / gradient live in a wider
     concat buffer; `acc`: the input gradient is added to one that has already arrived."""
     import torch.nn.functional as F
