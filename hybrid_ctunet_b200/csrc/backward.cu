@@ -553,26 +553,42 @@ __global__ void __launch_bounds__(256) cf_to_cl_kernel(const float* __restrict__
 // Space-to-depth: in [B][X*u3][Y*u2][Z*u1][ldi] (C channels) -> out [B][X][Y][Z][u3*u2*u1*C] with column
 // (sub*C + c), sub = (a3*u2 + a2)*u1 + a1 — the gradient of a kernel==stride transposed convolution / pixel
 // shuffle arranged as the plain-GEMM output it was in the forward.
+// IDX = unsigned when every row / element count fits 32 bits (the 64-bit divisions otherwise dominate the copy), two
+// 16-byte elements in flight per thread.
+template <typename IDX>
 __global__ void __launch_bounds__(256) space_to_depth_kernel(const __nv_bfloat16* __restrict__ in, int ldi,
                                                              __nv_bfloat16* __restrict__ out, int B, int X, int Y, int Z,
                                                              int u3, int u2, int u1, int C) {
-  const int tpr = C / 8;
-  const int k3 = u1 * u2 * u3;
-  const long long total = (long long)B * X * Y * Z * k3 * tpr;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long r = i / tpr;
+  const IDX tpr = (IDX)(C / 8);
+  const IDX k3 = (IDX)(u1 * u2 * u3);
+  const IDX total = (IDX)B * X * Y * Z * k3 * tpr;
+  const IDX step = (IDX)gridDim.x * blockDim.x;
+  auto src_of = [&](IDX i, long long& dst) -> const uint4* {
+    const IDX r = i / tpr;
     const int cv = (int)(i - r * tpr);
-    const int sub = (int)(r % k3);
-    const long long orow = r / k3;
-    long long t = orow;
-    const int z = (int)(t % Z); t /= Z;
-    const int y = (int)(t % Y); t /= Y;
-    const int x = (int)(t % X);
-    const int b = (int)(t / X);
+    const IDX orow = r / k3;
+    const int sub = (int)(r - orow * k3);
+    IDX t = orow;
+    const IDX tz = t / (IDX)Z;
+    const int z = (int)(t - tz * (IDX)Z); t = tz;
+    const IDX ty = t / (IDX)Y;
+    const int y = (int)(t - ty * (IDX)Y); t = ty;
+    const IDX b = t / (IDX)X;
+    const int x = (int)(t - b * (IDX)X);
     const int a1 = sub % u1, a2 = (sub / u1) % u2, a3 = sub / (u1 * u2);
     const long long irow = (((long long)b * X * u3 + (x * u3 + a3)) * (Y * u2) + (y * u2 + a2)) * (Z * u1) + (z * u1 + a1);
-    *reinterpret_cast<uint4*>(out + (orow * k3 + sub) * (long long)C + cv * 8) =
-        *reinterpret_cast<const uint4*>(in + irow * ldi + cv * 8);
+    dst = (long long)r * C + cv * 8;
+    return reinterpret_cast<const uint4*>(in + irow * ldi + cv * 8);
+  };
+  for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * step) {
+    long long d0, d1 = 0;
+    const uint4* s0 = src_of(i, d0);
+    const bool two = i + step < total;
+    const uint4* s1 = two ? src_of(i + step, d1) : s0;
+    const uint4 v0 = *s0;
+    const uint4 v1 = *s1;
+    *reinterpret_cast<uint4*>(out + d0) = v0;
+    if (two) *reinterpret_cast<uint4*>(out + d1) = v1;
   }
 }
 
@@ -957,8 +973,12 @@ extern "C" int ctu_space_to_depth(const void* in, int ldi, void* out, int B, int
                                   int C, void* stream) {
   if (!in || !out || C % 8 || ldi % 8 || u1 < 1 || u2 < 1 || u3 < 1) return CTU_E_BADARG;
   const long long total = (long long)B * X * Y * Z * u1 * u2 * u3 * (C / 8);
-  space_to_depth_kernel<<<bw_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)in, ldi, (bf16*)out, B, X, Y, Z,
-                                                                               u3, u2, u1, C);
+  if (total < 0x7fffffffLL)
+    space_to_depth_kernel<unsigned><<<bw_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)in, ldi, (bf16*)out, B, X,
+                                                                                         Y, Z, u3, u2, u1, C);
+  else
+    space_to_depth_kernel<long long><<<bw_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)in, ldi, (bf16*)out, B,
+                                                                                          X, Y, Z, u3, u2, u1, C);
   count_launch();
   return (int)cudaGetLastError();
 }
