@@ -103,3 +103,19 @@ def test_oracle_blend_on_cpu_small():
     assert torch.allclose(a, x.repeat(1, 3, 1, 1, 1), atol=1e-6) and torch.allclose(b, 2 * a, atol=1e-6)
     c = O.sliding_window_inference(x, (32, 32, 32), 2, lambda w: (w,), overlap=0.25, two_heads=False)  # roi > image: pad+crop
     assert c.shape == x.shape and torch.allclose(c, x, atol=1e-6)
+
+
+def test_shard_window_range_partitions_in_whole_calls():
+    """Sharded sliding window: contiguous, disjoint chunks that cover the window list, every chunk but the last non-empty one a
+    whole number of sw_batch calls; ranks beyond the work get an empty range."""
+    from hybrid_ctunet_b200.sliding_window import shard_window_range
+    for total, sw, world in ((500, 4, 8), (500, 4, 2), (500, 4, 4), (1792, 4, 8), (1, 4, 2), (7, 4, 8), (64, 4, 3), (10, 1, 4), (9, 4, 1)):
+        ranges = [shard_window_range(total, sw, world, r) for r in range(world)]
+        assert ranges[0][0] == 0 and max(hi for _, hi in ranges) == total
+        for (lo, hi), (lo2, _) in zip(ranges, ranges[1:]):
+            assert lo <= hi and hi == lo2
+        nonempty = [(lo, hi) for lo, hi in ranges if hi > lo]
+        assert all((hi - lo) % sw == 0 for lo, hi in nonempty[:-1])
+        calls = [-(-(hi - lo) // sw) for lo, hi in ranges]
+        assert max(calls) == -(-(-(-total // sw)) // world)          # the slowest rank runs ceil(calls / world) calls
+    assert [shard_window_range(500, 4, 8, r) for r in (0, 6, 7)] == [(0, 64), (384, 448), (448, 500)]
