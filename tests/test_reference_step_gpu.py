@@ -251,7 +251,8 @@ def _sw_worker(rank, world, port, out):
     try:
         pred = lambda w: ((torch.sin(3 * w).repeat(1, 5, 1, 1, 1),), (torch.cos(2 * w).repeat(1, 5, 1, 1, 1),))
         res = {}
-        for name, shape in (("one_window", (1, 1, 32, 32, 32)), ("three_windows", (1, 1, 32, 32, 64))):
+        for name, shape in (("one_window", (1, 1, 32, 32, 32)), ("three_windows", (1, 1, 32, 32, 64)),
+                            ("nine_windows", (1, 1, 32, 32, 160))):
             g = torch.Generator(device="cuda").manual_seed(9)
             vol = torch.rand(*shape, device="cuda", generator=g)
             a0, a1 = sliding_window_inference(vol, (32, 32, 32), 4, pred, overlap=0.5, mode="gaussian",
@@ -264,14 +265,16 @@ def _sw_worker(rank, world, port, out):
 
 def test_sharded_sliding_window_with_fewer_windows_than_ranks(tmp_path):
     """a rank that owns no window (volume <= roi on 2 ranks) joins the collectives with zero
-    accumulators instead of raising while its peers wait in the all-reduce; every rank returns the full result."""
+    accumulators instead of raising while its peers wait in the all-reduce; every rank returns the full result.  Nine windows
+    at sw_batch 4 on 2 ranks: chunks of whole calls (8 + 1 windows, sliding_window.shard_window_range)."""
     import torch.multiprocessing as mp
     from hybrid_ctunet_b200.trainer_CTUNet import sliding_window_inference
     out = str(tmp_path / "sw")
     mp.spawn(_sw_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     r0, r1 = torch.load(out + ".0"), torch.load(out + ".1")
     pred = lambda w: ((torch.sin(3 * w).repeat(1, 5, 1, 1, 1),), (torch.cos(2 * w).repeat(1, 5, 1, 1, 1),))
-    for name, shape in (("one_window", (1, 1, 32, 32, 32)), ("three_windows", (1, 1, 32, 32, 64))):
+    for name, shape in (("one_window", (1, 1, 32, 32, 32)), ("three_windows", (1, 1, 32, 32, 64)),
+                            ("nine_windows", (1, 1, 32, 32, 160))):
         g = torch.Generator(device="cuda").manual_seed(9)
         vol = torch.rand(*shape, device="cuda", generator=g)
         s0, s1 = sliding_window_inference(vol, (32, 32, 32), 4, pred, overlap=0.5, mode="gaussian")
